@@ -132,8 +132,11 @@ class Reference:
         self.L.dktref_init(self.dim, self.max_depth)
 
     def tables(self):
-        nrot = self.L.dktref_tables(self.dim, None, None)
         nch = 1 << self.dim
+        if not self.L.dktref_is_hilbert():  # Morton build: one identity rotation (src/KDhcurvedata.cpp:47-57)
+            ident = np.arange(nch, dtype=np.int8)[None, :]
+            return np.concatenate([ident, ident], axis=1), np.zeros((1, nch), dtype=np.int32)
+        nrot = self.L.dktref_tables(self.dim, None, None)
         rot = np.zeros(nrot, dtype=np.int8)
         htab = np.zeros(nrot // 2, dtype=np.int32)
         self.L.dktref_tables(self.dim, _p(rot), _p(htab))
