@@ -1,0 +1,231 @@
+// C ABI of libdkt.so (declared in include/dkt.h).
+#include "dkt_internal.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace dkt
+{
+static thread_local std::string g_err;
+uint64_t g_launches = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+
+// exact parent->child 1-D interpolation on uniform nodes in [-1,1] (what RefElement's ip_1D_0/1
+// approximate, FEM/src/refel.cpp:112-163): A[k*M+j] = l_k(x_j^child), Lagrange basis l_k.
+static void exact_interp(int order, double ip[2][MAX_M * MAX_M])
+{
+  const int M = order + 1;
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < M; k++)
+      for (int j = 0; j < M; j++)
+      {
+        const double xj = -1.0 + 2.0 * j / order;
+        const double xc = 0.5 * (xj + (b ? 1.0 : -1.0));
+        double l = 1.0;
+        for (int m = 0; m < M; m++)
+          if (m != k)
+          {
+            const double xm = -1.0 + 2.0 * m / order, xk = -1.0 + 2.0 * k / order;
+            l *= (xc - xm) / (xk - xm);
+          }
+        ip[b][k * M + j] = l;
+      }
+}
+} // namespace dkt
+
+using namespace dkt;
+
+struct dkt_da
+{
+  DA d;
+};
+
+#define CKA(call)                                                                                 \
+  do                                                                                              \
+  {                                                                                               \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+    {                                                                                             \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+      return DKT_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+extern "C"
+{
+  const char *dkt_last_error(void) { return g_err.c_str(); }
+  const char *dkt_version(void) { return "dkt-b200 0.1 (sm_100a)"; }
+  uint64_t dkt_kernel_launch_count(void) { return g_launches; }
+
+  int dkt_sfc_tables(int dim, int sfc_mode, char *rotations, int *hilbert_table)
+  {
+    if (dim < 2 || dim > 4 || (sfc_mode != DKT_SFC_MORTON && sfc_mode != DKT_SFC_HILBERT)) return -1;
+    SfcTables t;
+    make_sfc_tables(dim, sfc_mode, t);
+    const int nch = t.nch;
+    for (int r = 0; r < t.nrot; r++)
+      for (int i = 0; i < nch; i++)
+      {
+        if (rotations)
+        {
+          rotations[r * 2 * nch + i] = (char)t.rot_perm[r * nch + i];
+          rotations[r * 2 * nch + nch + i] = (char)t.rot_inv[r * nch + i];
+        }
+        if (hilbert_table) hilbert_table[r * nch + i] = t.htab[r * nch + i];
+      }
+    return t.nrot;
+  }
+
+  int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
+                    uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out)
+  {
+    if (!out) { set_error("out is NULL"); return DKT_ERR_INVALID; }
+    *out = nullptr;
+    if (dim < 2 || dim > 4) { set_error("dim must be 2, 3 or 4"); return DKT_ERR_INVALID; }
+    if (order < 1 || order > 2) { set_error("order must be 1 or 2 (low-order node resolver, include/nsort.tcc:1267)"); return DKT_ERR_UNSUPPORTED; }
+    if (dim == 4 && order == 2) { set_error("4-D order 2 (81 nodes per element) has no kernel yet"); return DKT_ERR_UNSUPPORTED; }
+    if (max_depth < 1 || max_depth > 30) { set_error("max_depth must be in 1..30"); return DKT_ERR_INVALID; }
+    if (sfc_mode != DKT_SFC_MORTON && sfc_mode != DKT_SFC_HILBERT) { set_error("bad sfc_mode"); return DKT_ERR_INVALID; }
+    if (!elem_xyz || !elem_lev) { set_error("element arrays are NULL"); return DKT_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+      set_error("no CUDA device: libdkt has no CPU path");
+      return DKT_ERR_CUDA;
+    }
+    dkt_da *h = new (std::nothrow) dkt_da;
+    if (!h) { set_error("out of host memory"); return DKT_ERR_INVALID; }
+    DA &d = h->d;
+    d.dim = dim; d.order = order; d.max_depth = max_depth; d.sfc_mode = sfc_mode;
+    d.M = order + 1;
+    d.N = 1;
+    for (int i = 0; i < dim; i++) d.N *= d.M;
+    if ((ip0 == nullptr) != (ip1 == nullptr)) { delete h; set_error("ip0 and ip1 must both be given or both NULL"); return DKT_ERR_INVALID; }
+    if (ip0)
+    {
+      std::memcpy(d.ip[0], ip0, sizeof(double) * d.M * d.M);
+      std::memcpy(d.ip[1], ip1, sizeof(double) * d.M * d.M);
+    }
+    else
+      exact_interp(order, d.ip);
+    const int rc = build_da(d, elem_xyz, elem_lev, n_elem, flags);
+    if (rc != DKT_OK)
+    {
+      const std::string keep = g_err;
+      free_da(d);
+      delete h;
+      g_err = keep;
+      return rc;
+    }
+    *out = h;
+    return DKT_OK;
+  }
+
+  int dkt_da_destroy(dkt_da *da)
+  {
+    if (!da) return DKT_OK;
+    cudaSetDevice(da->d.device);
+    free_da(da->d);
+    delete da;
+    return DKT_OK;
+  }
+
+  int dkt_da_sizes(const dkt_da *da, dkt_sizes *s)
+  {
+    if (!da || !s) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    const DA &d = da->d;
+    std::memset(s, 0, sizeof(*s));
+    s->n_elem = d.nElem; s->n_mv_elem = d.nMv; s->n_nodes = d.nNodes; s->n_boundary = d.nBdy; s->n_hanging = d.nHang;
+    s->n_split = d.nSplit; s->nodes_per_elem = d.N; s->tree_class = d.tree_class; s->finest_level = d.finest_level;
+    // read u + write v, the uint32 element->node table, and per hanging element
+    // the parent-cell node ids + child number/masks
+    s->alg_bytes = d.nNodes * 16ull + d.nMv * (uint64_t)d.N * 4ull + d.nHang * ((uint64_t)d.N * 4ull + 8ull);
+    return DKT_OK;
+  }
+
+#define D2H(dst, src, bytes)                                                              \
+  do                                                                                      \
+  {                                                                                       \
+    if ((dst) && (bytes) > 0) CKA(cudaMemcpy((dst), (src), (bytes), cudaMemcpyDeviceToHost)); \
+  } while (0)
+
+  int dkt_da_export_elements(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
+  {
+    if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    const DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    D2H(xyz, d.d_elem_xyz, d.nElem * d.dim * sizeof(uint32_t));
+    D2H(lev, d.d_elem_lev, d.nElem);
+    return DKT_OK;
+  }
+  int dkt_da_export_nodes(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
+  {
+    if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    const DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    D2H(xyz, d.d_node_xyz, d.nNodes * d.dim * sizeof(uint32_t));
+    D2H(lev, d.d_node_lev, d.nNodes);
+    return DKT_OK;
+  }
+  int dkt_da_export_boundary(const dkt_da *da, uint32_t *ids)
+  {
+    if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    const DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    D2H(ids, d.d_bdy, d.nBdy * sizeof(uint32_t));
+    return DKT_OK;
+  }
+  int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, uint32_t *e2n, uint32_t *pnode, uint8_t *child)
+  {
+    if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    const DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    D2H(mv_xyz, d.d_mv_xyz, d.nMv * d.dim * sizeof(uint32_t));
+    D2H(mv_lev, d.d_mv_lev, d.nMv);
+    D2H(e2n, d.d_e2n, d.nMv * d.N * sizeof(uint32_t));
+    D2H(pnode, d.d_pnode, d.nHang * d.N * sizeof(uint32_t));
+    D2H(child, d.d_child, d.nHang);
+    return DKT_OK;
+  }
+
+  int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags)
+  {
+    if (!da || !op || !in || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    const size_t bytes = d.nNodes * sizeof(double);
+    const double *din = in;
+    double *dout = out;
+    if (!(flags & DKT_VEC_DEVICE))
+    {
+      if (!d.d_in)
+      {
+        CKA(cudaMalloc((void **)&d.d_in, bytes));
+        CKA(cudaMalloc((void **)&d.d_out, bytes));
+      }
+      CKA(cudaMemcpyAsync(d.d_in, in, bytes, cudaMemcpyHostToDevice, d.stream));
+      din = d.d_in;
+      dout = d.d_out;
+    }
+    CKA(cudaEventRecord(d.ev0, d.stream));
+    const int rc = run_matvec(d, op, din, dout, scale, flags);
+    if (rc != DKT_OK) return rc;
+    CKA(cudaEventRecord(d.ev1, d.stream));
+    if (!(flags & DKT_VEC_DEVICE))
+    {
+      CKA(cudaMemcpyAsync(out, d.d_out, bytes, cudaMemcpyDeviceToHost, d.stream));
+      CKA(cudaStreamSynchronize(d.stream));
+    }
+    return DKT_OK;
+  }
+
+  int dkt_last_kernel_ms(dkt_da *da, float *ms)
+  {
+    if (!da || !ms) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    CKA(cudaEventSynchronize(da->d.ev1));
+    CKA(cudaEventElapsedTime(ms, da->d.ev0, da->d.ev1));
+    return DKT_OK;
+  }
+  void *dkt_da_stream(dkt_da *da) { return da ? (void *)da->d.stream : nullptr; }
+}

@@ -1,0 +1,78 @@
+// Internal declarations shared by the translation units of libdkt.so (not installed).
+#ifndef DKT_INTERNAL_H
+#define DKT_INTERNAL_H
+
+#include "../../include/dkt.h"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+typedef struct CUstream_st *cudaStream_t;
+typedef struct CUevent_st *cudaEvent_t;
+#endif
+
+namespace dkt
+{
+constexpr uint32_t INVALID = 0xFFFFFFFFu;
+constexpr int MAX_NPE = 27;   // nodes per element handled by the register kernels (3-D p=2)
+constexpr int MAX_M = 3;      // order + 1
+
+struct SfcTables
+{
+  int dim = 0, nch = 0, nrot = 0;
+  std::vector<uint8_t> rot_perm, rot_inv, htab;
+};
+void make_sfc_tables(int dim, int mode, SfcTables &t);
+
+void set_error(const std::string &msg);
+extern uint64_t g_launches;
+
+// Everything one rank needs on the device.  All d_* pointers are device memory.
+struct DA
+{
+  int dim = 0, order = 0, max_depth = 0, sfc_mode = 0;
+  int N = 0, M = 0;
+  int finest_level = 0;  // finest element level
+  int lk = 0;            // finest lattice level (finest_level + 1 for order 2)
+  int shift = 0, bits = 0;
+  int tree_class = 0;
+  int device = 0;
+  uint64_t nElem = 0, nMv = 0, nReg = 0, nHang = 0, nNodes = 0, nExtNodes = 0, nBdy = 0, nSplit = 0, nU = 0;
+
+  uint32_t *d_elem_xyz = nullptr;  // [nElem*dim] AoS, tree order
+  uint8_t *d_elem_lev = nullptr;
+  uint32_t *d_node_xyz = nullptr;  // [nNodes*dim] DA order
+  uint8_t *d_node_lev = nullptr;
+  uint32_t *d_bdy = nullptr;       // [nBdy]
+  uint8_t *d_node_isbdy = nullptr; // [nNodes]
+
+  // visited elements: regular ones first [0,nReg), hanging ones after [nReg,nMv)
+  uint32_t *d_e2n = nullptr;       // [nMv*N]
+  uint32_t *d_mv_xyz = nullptr;    // [nMv*dim]
+  uint8_t *d_mv_lev = nullptr;     // [nMv]
+  uint32_t *d_mv_src = nullptr;    // [nMv] position in SFC visit order (for export)
+  uint32_t *d_pnode = nullptr;     // [nHang*N]
+  uint8_t *d_child = nullptr;      // [nHang]
+
+  // coordinate -> node lookup: sorted unique packed keys of all lattice locations
+  uint64_t *d_ukey = nullptr;      // [nU]
+  uint32_t *d_unode = nullptr;     // [nU] node id or INVALID (hanging location)
+
+  double ip[2][MAX_M * MAX_M];     // parent->child 1-D matrices, A[k*M+j]
+
+  double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+};
+
+int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t n, unsigned flags);
+void free_da(DA &da);
+int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+} // namespace dkt
+
+#endif

@@ -1,0 +1,137 @@
+/* dkt.h - C ABI of libdkt.so: the B200-native matrix-free FE matvec on adaptive k-D SFC trees.
+ *
+ * This is the drop-in boundary for ONE path of paralab/Dendro-KT: everything between
+ * `ot::DA<dim>` construction from a balanced linear tree and `feMatrix<LeafT,dim>::matVec`.
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository).  Plain pointers and sizes only; no exceptions cross this boundary;
+ * every function returns an int status (DKT_OK == 0) and dkt_last_error() describes the
+ * most recent failure on the calling thread.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a).
+ */
+#ifndef DKT_H
+#define DKT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKT_OK 0
+#define DKT_ERR_INVALID 1   /* bad argument                                              */
+#define DKT_ERR_CUDA 2      /* CUDA runtime / driver failure (no device, OOM, ...)       */
+#define DKT_ERR_UNSUPPORTED 3
+#define DKT_ERR_UNDEFINED_TREE 4 /* class-U tree: the reference reads undefined values   */
+#define DKT_ERR_NCCL 5
+
+/* SFC used for the element order and inside the node order (CMake option HILBERT_ORDERING,
+ * src/KDhcurvedata.cpp:24-59).  The reference's default build is Morton. */
+#define DKT_SFC_MORTON 0
+#define DKT_SFC_HILBERT 1
+
+/* dkt_da_create flags */
+#define DKT_ELEMS_ON_DEVICE 1u  /* elem_xyz / elem_lev are device pointers                  */
+#define DKT_ELEMS_PRESORTED 2u  /* elements already in tree order (skip the SFC sort)        */
+#define DKT_ALLOW_UNDEFINED 4u  /* build class-U trees anyway (intended semantics, unpinned) */
+
+/* dkt_matvec flags */
+#define DKT_VEC_HOST 0u    /* in/out are host pointers: H2D, matvec, D2H                    */
+#define DKT_VEC_DEVICE 1u  /* in/out are device pointers on the DA's device                */
+#define DKT_NO_Q1_MASK 2u  /* mathematically consistent transpose (NOT the reference's)    */
+
+/* tree classes */
+#define DKT_CLASS_A 0 /* no hanging nodes                                                  */
+#define DKT_CLASS_B 1 /* hanging nodes, none on the domain boundary                        */
+#define DKT_CLASS_P 2 /* boundary hanging nodes kept as DOFs -> phantom child elements      */
+#define DKT_CLASS_U 3 /* reference reads undefined parent values (FEM/include/matvec.h:439) */
+
+/* elemental operator kinds */
+#define DKT_OP_IDENTITY 0 /* out = in  (test/testMatvec.cpp:177-198)                        */
+#define DKT_OP_DENSE 1    /* out = scale * 2^(-alpha*level) * kref * in                     */
+
+typedef struct dkt_da dkt_da;
+
+/* Device form of the user's `elementalMatVec(const VECType*in, VECType*out, double*coords,
+ * double scale)` (FEM/include/feMatrix.h:56).  The host callback cannot run per element on the
+ * GPU; a leaf class maps to one of these (and the C++ layer verifies the mapping against the
+ * callback on sample elements).  For axis-aligned cells K_e depends only on the level. */
+typedef struct dkt_op
+{
+  int kind;            /* DKT_OP_*                                                           */
+  const double *kref;  /* host pointer, N*N row-major: out[i] = sum_j kref[i*N+j]*in[j]      */
+  double alpha;        /* level exponent: K_e = scale * 2^(-alpha*L) * kref                 */
+  int dirichlet;       /* 1: zero domain-boundary entries of input and output, like
+                          HeatMat::preMatVec/postMatVec (FEM/examples/src/heatMat.cpp:120-139) */
+} dkt_op;
+
+typedef struct dkt_sizes
+{
+  uint64_t n_elem;       /* tree elements (leaves)                                           */
+  uint64_t n_mv_elem;    /* elements the matvec visits (phantom children included)           */
+  uint64_t n_nodes;      /* CG nodes == DA::getTotalNodalSz() on one rank                   */
+  uint64_t n_boundary;   /* DA::getBoundaryNodeIndices().size()                              */
+  uint64_t n_hanging;    /* visited elements with at least one hanging lattice node          */
+  uint64_t n_split;      /* tree elements replaced by phantom children (class P)             */
+  uint64_t alg_bytes;    /* algorithmic bytes of one matvec (SURVEY.md §8d formula)          */
+  int nodes_per_elem;    /* (order+1)^dim                                                    */
+  int tree_class;        /* DKT_CLASS_*                                                      */
+  int finest_level;
+  int reserved;
+} dkt_sizes;
+
+const char *dkt_last_error(void);
+const char *dkt_version(void);
+
+/* SFC tables in the reference's layout (include/hcurvedata.h:49-59): rotations[r*2*2^dim + i]
+ * = rot_perm (i < 2^dim) | rot_inv, hilbert_table[r*2^dim + child_m] = child rotation.
+ * Generated from first principles (no table data is taken from the reference); the state
+ * numbering differs from KDhcurvedata_DATA.cpp but the curve is the same.  Returns the number
+ * of rotations; pass NULL outputs to query it.  Replaces _InitializeHcurve(dim). */
+int dkt_sfc_tables(int dim, int sfc_mode, char *rotations, int *hilbert_table);
+
+/* Replaces ot::DA<dim>::DA(const TreeNode*inTree, nEle, comm, order, ...) (include/oda.h:150,
+ * src/oda.cpp:46-151) for a single rank.  inTree is passed as anchors elem_xyz[n_elem*dim]
+ * (units of 2^-max_depth, i.e. TreeNode::getX(d)) and levels elem_lev[n_elem]; it must be a
+ * 2:1-balanced complete linear tree.  ip0/ip1: RefElement::getIMChild0()/getIMChild1()
+ * ((order+1)^2 doubles each, FEM/include/refel.h:187-188) or NULL for exact interpolation.
+ * Builds on the current CUDA device: tree order (SFC_Tree::locTreeSort), the CG node set and
+ * its order (SFC_NodeSort::dist_countCGNodes), element->node and hanging-node tables. */
+int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
+                  uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out);
+int dkt_da_destroy(dkt_da *da);
+
+int dkt_da_sizes(const dkt_da *da, dkt_sizes *out);
+/* tree in DA order: what DA::getTreePartFront()/Back() bracket (include/oda.h:255-258) */
+int dkt_da_export_elements(const dkt_da *da, uint32_t *xyz, uint8_t *lev);
+/* DA::getTNCoords() (include/oda.h:252): node coordinates and levels in DA order */
+int dkt_da_export_nodes(const dkt_da *da, uint32_t *xyz, uint8_t *lev);
+/* DA::getBoundaryNodeIndices() (include/oda.h:264) */
+int dkt_da_export_boundary(const dkt_da *da, uint32_t *ids);
+/* flat tables (no reference counterpart - the reference re-discovers them every matvec,
+ * FEM/include/matvec.h:244-548).  Visited elements are stored regular-first: entries
+ * [0, n_mv_elem - n_hanging) have every lattice node, the last n_hanging have hanging nodes.
+ * mv_xyz[n_mv_elem*dim], mv_lev[n_mv_elem], e2n[n_mv_elem*N] (0xFFFFFFFF = hanging),
+ * pnode[n_hanging*N] (0xFFFFFFFF = absent or level != L-1), child[n_hanging].
+ * Any pointer may be NULL. */
+int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, uint32_t *e2n, uint32_t *pnode,
+                         uint8_t *child);
+
+/* Replaces feMatrix<LeafT,dim>::matVec(const VECType*in, VECType*out, double scale)
+ * (FEM/include/feMatrix.h:190-259) including fem::matvec (FEM/include/matvec.h:232) for one
+ * rank.  in/out have n_nodes doubles in DA order. */
+int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags);
+
+/* Device time of the kernels of the most recent dkt_matvec on this DA, in milliseconds
+ * (CUDA events on the DA's stream; excludes H2D/D2H). */
+int dkt_last_kernel_ms(dkt_da *da, float *ms);
+/* The CUDA stream (cudaStream_t) the DA launches on, for callers that time with events. */
+void *dkt_da_stream(dkt_da *da);
+/* Number of kernels launched by this library in the calling process since load. */
+uint64_t dkt_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,155 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle restatement and the
+golden vectors taken from the reference.  Integer tables bit-exact; fp64 vectors within 1e-12
+relative (the tolerance BASELINE.json's north_star states)."""
+import numpy as np
+import pytest
+
+import cases
+import flat
+from test_oracle import load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _sfc(dkt, case):
+    return dkt.SFC_HILBERT if case["sfc"] == "hilbert" else dkt.SFC_MORTON
+
+
+def _sorted_rows(xyz, lev, *cols):
+    """Canonical row order (level, coordinates) to compare element tables stored in different orders."""
+    key = np.lexsort(tuple(xyz[:, d] for d in range(xyz.shape[1])) + (lev,))
+    return [c[key] for c in (xyz, lev) + cols]
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_tables_and_matvec_match_reference(dkt, name):
+    case = load_case(name)
+    g = case["golden"]
+    da = dkt.DA(case["xyz"], case["lev"], case["dim"], case["order"], case["max_depth"], sfc=_sfc(dkt, case), ip0=g["ip0"],
+                ip1=g["ip1"])
+    # --- construction-time tables: bit-exact against the reference -------------------------------
+    exyz, elev = da.elements()
+    assert np.array_equal(exyz, g["elem_xyz"]) and np.array_equal(elev, g["elem_lev"])
+    nxyz, nlev = da.nodes()
+    assert np.array_equal(nxyz, g["node_xyz"]), "CG node order differs from DA::getTNCoords()"
+    assert np.array_equal(nlev, g["node_lev"])
+    assert np.array_equal(da.boundary_ids(), g["bdy"])
+    assert da.n_mv_elem == int(g["ncalls"])
+    # --- flat tables against the oracle ------------------------------------------------------------
+    t = cases.oracle_tables_for(case)
+    assert da.tree_class == t.tree_class
+    tb = da.tables()
+    oe2n = np.where(t.e2n < 0, dkt.INVALID, t.e2n).astype(np.uint32)
+    a = _sorted_rows(tb["mv_xyz"], tb["mv_lev"], tb["e2n"])
+    b = _sorted_rows(t.mv_xyz, t.mv_lev, oe2n)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    nh = da.n_hanging
+    assert nh == len(t.hang_idx)
+    if nh:
+        hx, hl = tb["mv_xyz"][-nh:], tb["mv_lev"][-nh:]
+        a = _sorted_rows(hx, hl, tb["pnode"], tb["child"])
+        op = np.where(t.pnode < 0, dkt.INVALID, t.pnode).astype(np.uint32)
+        b = _sorted_rows(t.mv_xyz[t.hang_idx], t.mv_lev[t.hang_idx], op, t.child.astype(np.uint8))
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # --- matvec against the reference's own output ---------------------------------------------------
+    n = da.n_nodes
+    K = cases.dense_operator(case["dim"], case["order"])
+    u = cases.input_vector(n)
+    v = da.matvec(dkt.Operator.dense(K, float(g["alpha"])), u, scale=float(g["scale"]))
+    assert np.abs(v - g["v_dense"]).max() <= TOL * np.abs(g["v_dense"]).max()
+    vd = da.matvec(dkt.Operator.dense(K, float(g["alpha"]), dirichlet=True), u, scale=float(g["scale"]))
+    assert np.abs(vd - g["v_dense_diri"]).max() <= TOL * np.abs(g["v_dense_diri"]).max()
+    vi = da.matvec(dkt.Operator.identity(), np.ones(n))
+    assert np.abs(vi - g["v_id"]).max() <= TOL * np.abs(g["v_id"]).max()
+    da.close()
+
+
+def test_device_pointer_path_and_repeatability(dkt):
+    import torch
+    dim, md = 3, 12
+    xyz, lev = dkt.trees.moving_ball_tree(dim, 7, md)
+    da = dkt.DA(xyz, lev, dim, 1, md)
+    t = flat.build_tables(xyz, lev, dim, 1, md)
+    K = flat.laplace_kref(dim, 1)
+    u = cases.input_vector(da.n_nodes)
+    vo = flat.matvec(t, u, K, alpha=dim - 2.0)
+    op = dkt.Operator.dense(K, dim - 2.0)
+    vh = da.matvec(op, u)
+    ud = torch.from_numpy(u).cuda()
+    vd = torch.empty_like(ud)
+    da.matvec(op, ud, vd)
+    torch.cuda.synchronize()
+    assert np.abs(vh - vo).max() <= TOL * np.abs(vo).max()
+    assert np.abs(vd.cpu().numpy() - vo).max() <= TOL * np.abs(vo).max()
+    assert da.last_kernel_ms() > 0
+    da.close()
+
+
+def test_elements_on_device_and_presorted(dkt):
+    import torch
+    dim, md = 4, 10
+    xyz, lev = dkt.trees.moving_ball_tree(dim, 5, md, use_torch=True)
+    da = dkt.DA(xyz, lev, dim, 1, md)
+    t = flat.build_tables(xyz.cpu().numpy().astype(np.uint32), lev.cpu().numpy(), dim, 1, md)
+    nx, nl = da.nodes()
+    assert np.array_equal(nx, t.node_xyz) and np.array_equal(nl, t.node_lev)
+    ex, el = da.elements()
+    da2 = dkt.DA(ex, el, dim, 1, md, presorted=True)
+    nx2, _ = da2.nodes()
+    assert np.array_equal(nx2, nx)
+    da.close()
+    da2.close()
+
+
+def test_properties_at_scale(dkt):
+    """Size-independent properties on a tree the oracle cannot reach in seconds (3-D uniform L7 =
+    2.1e6 elements and a 4-D ball with ~2e6 elements):
+    * Laplacian annihilates constants (also across hanging faces, interpolation is exact on them)
+    * linearity
+    * identity operator on a uniform tree counts incident elements: sum = 2^dim * nElem."""
+    import torch
+    for dim, xyz, lev, md in [(3,) + dkt.trees.uniform_tree_torch(3, 7, 12) + (12,),
+                              (4,) + dkt.trees.moving_ball_tree(4, 6, 10, use_torch=True) + (10,)]:
+        da = dkt.DA(xyz, lev, dim, 1, md)
+        K = flat.laplace_kref(dim, 1)
+        op = dkt.Operator.dense(K, dim - 2.0)
+        n = da.n_nodes
+        ones = torch.ones(n, dtype=torch.float64, device="cuda")
+        v = da.matvec(op, ones)
+        torch.cuda.synchronize()
+        assert float(v.abs().max()) < 1e-11
+        g = torch.Generator(device="cuda").manual_seed(1)
+        a = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        b = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        va, vb, vab = da.matvec(op, a), da.matvec(op, b), da.matvec(op, 2.0 * a - 3.0 * b)
+        torch.cuda.synchronize()
+        ref = 2.0 * va - 3.0 * vb
+        assert float((vab - ref).abs().max()) <= 1e-11 * float(ref.abs().max())
+        vi = da.matvec(dkt.Operator.identity(), ones)
+        torch.cuda.synchronize()
+        if da.tree_class == "A":
+            assert abs(float(vi.sum()) - (1 << dim) * da.n_elem) < 1e-6 * da.n_elem
+        da.close()
+
+
+def test_class_u_tree_is_refused(dkt):
+    """The stock testMovingBall sphere (test/testMovingBall.cpp:122-175) touches the domain
+    boundary with level jumps -> the reference reads undefined values; the library refuses."""
+    dim, md = 3, 10
+    xyz, lev = dkt.trees.moving_ball_tree(dim, 6, md, min_level=2, radius=0.36)
+    t = flat.build_tables(xyz, lev, dim, 1, md)
+    if t.tree_class != "U":
+        pytest.skip("generator did not produce a class-U tree")
+    with pytest.raises(dkt.DktError, match="class-U"):
+        dkt.DA(xyz, lev, dim, 1, md)
+    da = dkt.DA(xyz, lev, dim, 1, md, allow_undefined=True)
+    assert da.tree_class == "U"
+    da.close()
+
+
+def test_smoke_case(dkt):
+    import smoke_case
+    smoke_case.run(dkt)
