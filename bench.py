@@ -1,0 +1,227 @@
+#!/usr/bin/env python
+"""Benchmark of the matvec hot path (BASELINE.json: "matvec DOF/s (fp64, 4D p=1 adaptive)").
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU matvec
+
+One "step" = one matvec v = A u of the 4-D p=1 Laplacian on the class-B space-time moving-ball
+tree.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dendro-kt_b200"))
+
+METRIC = "matvec DOF/s (fp64, 4D p=1 adaptive)"
+UNIT = "DOF/s"
+DIM, ORDER, MAX_DEPTH = 4, 1, 12
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, level=5):
+    """The reference's own CPU matvec (oracle/_ref = the reference compiled here; single MPI rank,
+    single thread - the reference has no threading in this path) on a bounded sample of the
+    workload: the same moving-ball tree at a smaller refinement level."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import dkt
+    import dktref
+    from dkt import operators
+    if not dktref.available("morton"):
+        raise RuntimeError("oracle/_ref is not built")
+    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH)
+    R = dktref.Reference(DIM, MAX_DEPTH)
+    tree = R.tree_from_elements(xyz, lev, sort=True)
+    da = R.da(tree, ORDER)
+    K = operators.laplace_kref(DIM, ORDER)
+    u = np.random.default_rng(99).uniform(-1, 1, da.num_nodes)
+    _, secs, _ = da.matvec(u, dktref.OP_DENSE, K, alpha=DIM - 2.0, nwarm=warmup, niter=steps)
+    sample = "4-D p=1 moving-ball tree at max_level %d (%d elements, %d nodes), %d matvecs after %d warm-up" % (
+        level, len(lev), da.num_nodes, steps, warmup)
+    return da.num_nodes / secs, secs, sample, da.num_nodes, len(lev)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, secs, sample, n_nodes, n_elem = cpu_reference_run(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "4D p=1 Laplacian matvec, space-time moving-ball adaptive tree (class B), CPU sample", "dim": DIM,
+                   "order": ORDER, "n_elem": n_elem, "n_nodes": n_nodes},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import dkt
+    from dkt import operators
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        raise SystemExit("multi-GPU partitioning is not implemented yet in this revision")
+
+    level = args.level
+    t0 = time.time()
+    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH, use_torch=True)
+    torch.cuda.synchronize()
+    t_tree = time.time() - t0
+    t0 = time.time()
+    da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH)
+    t_build = time.time() - t0
+    del xyz, lev
+    torch.cuda.empty_cache()
+    K = operators.laplace_kref(DIM, ORDER)
+    op = dkt.Operator.dense(K, alpha=DIM - 2.0)
+    n = da.n_nodes
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    da.set_stream(stream.cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    u = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    v = torch.empty_like(u)
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for _ in range(args.warmup):
+        da.matvec(op, u, v)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dkt.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        da.matvec(op, u, v)
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    launches = dkt.kernel_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    ms = total_ms / args.steps
+    value = n / (ms * 1e-3)
+
+    # ---- end to end through the host API: pinned host buffers, H2D + matvec + D2H every step ----
+    uh = torch.empty(n, dtype=torch.float64).pin_memory()
+    vh = torch.empty(n, dtype=torch.float64).pin_memory()
+    uh.copy_(u.cpu())
+    un, vn = uh.numpy(), vh.numpy()
+    for _ in range(min(args.warmup, 3)):
+        da.matvec(op, un, vn)
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        da.matvec(op, un, vn)  # synchronous: returns after the D2H copy has landed
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    check = float(np.abs(vn - v.cpu().numpy()).max() / max(np.abs(vn).max(), 1e-300))
+
+    peaks, peak_kind = measured_peaks()
+    peak = float(peaks["hbm_gbs"])
+    achieved = da.alg_bytes / (ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "4D p=1 Laplacian matvec (dense 16x16 K_e = h^2 K_ref), space-time moving-ball adaptive tree, "
+                               "class B, max_level %d of max_depth %d" % (level, MAX_DEPTH),
+                   "dim": DIM, "order": ORDER, "n_elem": da.n_elem, "n_nodes": n, "n_hanging_elem": da.n_hanging,
+                   "tree_class": da.tree_class, "cache": "working set %.0f MB > 126 MB L2 (no flush needed)" % (da.alg_bytes / 1e6),
+                   "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
+                     "alg_bytes_per_step": da.alg_bytes, "kernel": "whole matvec step (memset + regular + hanging kernels)"},
+        "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "ms_per_step": e2e_s * 1e3, "max_rel_diff_vs_device_path": check},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "ms_per_step_min_max": [min(per_step), max(per_step)],
+    }
+    if args.cpu_baseline:
+        try:
+            cv, cs, sample, _, _ = cpu_reference_run(5, 2)
+            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
+        except Exception as e:  # the bench line must survive a missing oracle
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
+    print(json.dumps(line))
+    da.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dkt", choices=["dkt", "reference"])
+    ap.add_argument("--level", type=int, default=7, help="finest level of the moving-ball tree")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -228,4 +228,10 @@ extern "C"
     return DKT_OK;
   }
   void *dkt_da_stream(dkt_da *da) { return da ? (void *)da->d.stream : nullptr; }
+  int dkt_da_set_stream(dkt_da *da, void *cuda_stream)
+  {
+    if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    da->d.stream = cuda_stream ? (cudaStream_t)cuda_stream : da->d.own_stream;
+    return DKT_OK;
+  }
 }

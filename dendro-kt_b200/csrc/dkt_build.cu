@@ -581,7 +581,7 @@ void free_da(DA &da)
   cudaFree(da.d_in); cudaFree(da.d_out);
   if (da.ev0) cudaEventDestroy(da.ev0);
   if (da.ev1) cudaEventDestroy(da.ev1);
-  if (da.stream) cudaStreamDestroy(da.stream);
+  if (da.own_stream) cudaStreamDestroy(da.own_stream);
   da = DA();
 }
 
@@ -589,7 +589,8 @@ int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t
 {
   const int dim = da.dim;
   CK(cudaGetDevice(&da.device));
-  CK(cudaStreamCreateWithFlags(&da.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&da.own_stream, cudaStreamNonBlocking));
+  da.stream = da.own_stream;
   CK(cudaEventCreate(&da.ev0));
   CK(cudaEventCreate(&da.ev1));
   if (n == 0) { set_error("empty tree"); return DKT_ERR_INVALID; }

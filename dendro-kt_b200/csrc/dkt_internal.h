@@ -65,7 +65,8 @@ struct DA
   double ip[2][MAX_M * MAX_M];     // parent->child 1-D matrices, A[k*M+j]
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
+  cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
 };

@@ -128,6 +128,9 @@ int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, doub
 int dkt_last_kernel_ms(dkt_da *da, float *ms);
 /* The CUDA stream (cudaStream_t) the DA launches on, for callers that time with events. */
 void *dkt_da_stream(dkt_da *da);
+/* Launch on the caller's stream from now on (e.g. torch's current stream); NULL restores the
+ * DA's own stream.  The caller keeps the stream alive. */
+int dkt_da_set_stream(dkt_da *da, void *cuda_stream);
 /* Number of kernels launched by this library in the calling process since load. */
 uint64_t dkt_kernel_launch_count(void);
 
