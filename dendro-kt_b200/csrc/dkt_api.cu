@@ -109,7 +109,8 @@ extern "C"
     }
     else
       exact_interp(order, d.ip);
-    const int rc = build_da(d, elem_xyz, elem_lev, n_elem, flags);
+    int rc = build_da(d, elem_xyz, elem_lev, n_elem, flags);
+    if (rc == DKT_OK) rc = build_chunks(d);
     if (rc != DKT_OK)
     {
       const std::string keep = g_err;
@@ -209,7 +210,7 @@ extern "C"
       dout = d.d_out;
     }
     CKA(cudaEventRecord(d.ev0, d.stream));
-    const int rc = run_matvec(d, op, din, dout, scale, flags);
+    const int rc = (flags & DKT_MV_FLAT) ? run_matvec(d, op, din, dout, scale, flags) : run_matvec_chunked(d, op, din, dout, scale, flags);
     if (rc != DKT_OK) return rc;
     CKA(cudaEventRecord(d.ev1, d.stream));
     if (!(flags & DKT_VEC_DEVICE))

@@ -573,8 +573,11 @@ static int flag_positions(DA &da, const uint8_t *flag, int mask, uint64_t n, Buf
   return DKT_OK;
 }
 
+int device_exclusive_scan(DA &da, const uint64_t *in, uint64_t *out, uint64_t n) { return exclusive_scan(da, in, out, n); }
+
 void free_da(DA &da)
 {
+  free_chunks(da);
   cudaFree(da.d_elem_xyz); cudaFree(da.d_elem_lev); cudaFree(da.d_node_xyz); cudaFree(da.d_node_lev);
   cudaFree(da.d_bdy); cudaFree(da.d_node_isbdy); cudaFree(da.d_e2n); cudaFree(da.d_mv_lev); cudaFree(da.d_mv_src);
   cudaFree(da.d_mv_xyz); cudaFree(da.d_pnode); cudaFree(da.d_child); cudaFree(da.d_ukey); cudaFree(da.d_unode);

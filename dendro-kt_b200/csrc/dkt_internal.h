@@ -31,6 +31,20 @@ void make_sfc_tables(int dim, int mode, SfcTables &t);
 void set_error(const std::string &msg);
 extern uint64_t g_launches;
 
+// One set of element chunks for the shared-memory matvec (dkt_chunks.cu).
+struct ChunkSet
+{
+  int rows = 1;                  // slot rows per element: 1 regular, 2 hanging (own + parent lattice)
+  uint64_t nElem = 0;
+  uint32_t nChunks = 0, elemsPerChunk = 0, maxNloc = 0, maxLen = 0, jdStride = 0;
+  uint64_t totalNodes = 0;
+  uint32_t *d_slot = nullptr;    // [nChunks*elemsPerChunk*rows*N] node rank | position << 16, rank-major per chunk
+  uint32_t *d_gid = nullptr;     // [totalNodes] global node id, chunk by chunk, (len desc) order inside a chunk
+  uint16_t *d_meta = nullptr;    // [totalNodes] run length | boundary bit | shared bit
+  uint16_t *d_jd = nullptr;      // [nChunks*jdStride] jagged-diagonal offsets
+  uint64_t *d_node_off = nullptr;// [nChunks+1]
+};
+
 // Everything one rank needs on the device.  All d_* pointers are device memory.
 struct DA
 {
@@ -41,6 +55,7 @@ struct DA
   int shift = 0, bits = 0;
   int tree_class = 0;
   int device = 0;
+  int numSMs = 0;
   uint64_t nElem = 0, nMv = 0, nReg = 0, nHang = 0, nNodes = 0, nExtNodes = 0, nBdy = 0, nSplit = 0, nU = 0;
 
   uint32_t *d_elem_xyz = nullptr;  // [nElem*dim] AoS, tree order
@@ -64,6 +79,8 @@ struct DA
 
   double ip[2][MAX_M * MAX_M];     // parent->child 1-D matrices, A[k*M+j]
 
+  ChunkSet reg, hang;              // chunked tables of elements [0,nReg) and [nReg,nMv)
+
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
   cudaStream_t own_stream = nullptr;
@@ -74,6 +91,10 @@ struct DA
 int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t n, unsigned flags);
 void free_da(DA &da);
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+int build_chunks(DA &da);
+void free_chunks(DA &da);
+int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+int device_exclusive_scan(DA &da, const uint64_t *in, uint64_t *out, uint64_t n);
 } // namespace dkt
 
 #endif

@@ -40,6 +40,8 @@ extern "C" {
 #define DKT_VEC_HOST 0u    /* in/out are host pointers: H2D, matvec, D2H                    */
 #define DKT_VEC_DEVICE 1u  /* in/out are device pointers on the DA's device                */
 #define DKT_NO_Q1_MASK 2u  /* mathematically consistent transpose (NOT the reference's)    */
+#define DKT_MV_FLAT 4u     /* use the flat gather/atomic kernels instead of the chunked ones */
+#define DKT_MV_NO_FASTPATH 8u /* apply kref as a dense matrix even if it has Walsh-Hadamard diagonal form */
 
 /* tree classes */
 #define DKT_CLASS_A 0 /* no hanging nodes                                                  */

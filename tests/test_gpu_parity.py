@@ -58,12 +58,38 @@ def test_tables_and_matvec_match_reference(dkt, name):
     n = da.n_nodes
     K = cases.dense_operator(case["dim"], case["order"])
     u = cases.input_vector(n)
-    v = da.matvec(dkt.Operator.dense(K, float(g["alpha"])), u, scale=float(g["scale"]))
-    assert np.abs(v - g["v_dense"]).max() <= TOL * np.abs(g["v_dense"]).max()
-    vd = da.matvec(dkt.Operator.dense(K, float(g["alpha"]), dirichlet=True), u, scale=float(g["scale"]))
-    assert np.abs(vd - g["v_dense_diri"]).max() <= TOL * np.abs(g["v_dense_diri"]).max()
-    vi = da.matvec(dkt.Operator.identity(), np.ones(n))
-    assert np.abs(vi - g["v_id"]).max() <= TOL * np.abs(g["v_id"]).max()
+    for flat_path in (False, True):  # the chunked (production) kernels and the flat ones
+        v = da.matvec(dkt.Operator.dense(K, float(g["alpha"])), u, scale=float(g["scale"]), flat=flat_path)
+        assert np.abs(v - g["v_dense"]).max() <= TOL * np.abs(g["v_dense"]).max()
+        vd = da.matvec(dkt.Operator.dense(K, float(g["alpha"]), dirichlet=True), u, scale=float(g["scale"]), flat=flat_path)
+        assert np.abs(vd - g["v_dense_diri"]).max() <= TOL * np.abs(g["v_dense_diri"]).max()
+        vi = da.matvec(dkt.Operator.identity(), np.ones(n), flat=flat_path)
+        assert np.abs(vi - g["v_id"]).max() <= TOL * np.abs(g["v_id"]).max()
+    # the mathematically consistent variant (no Q1 mask) agrees with the oracle's
+    v2 = da.matvec(dkt.Operator.dense(K, float(g["alpha"])), u, scale=float(g["scale"]), q1_mask=False)
+    vo2 = flat.matvec(t, u, K, alpha=float(g["alpha"]), scale=float(g["scale"]), ip0=g["ip0"], ip1=g["ip1"], q1_mask=False)
+    assert np.abs(v2 - vo2).max() <= TOL * np.abs(vo2).max()
+    da.close()
+
+
+@pytest.mark.parametrize("name", ["ball-d2-p1-morton-7", "ball-d3-p1-morton-6", "ball-d4-p1-morton-5", "gauss-d4-p1-morton"])
+def test_structured_operator_fast_path(dkt, name):
+    """Laplacian / mass / Helmholtz reference matrices have Walsh-Hadamard diagonal form at order 1;
+    the library applies them in that form.  Same answer as the dense product and as the oracle."""
+    case = load_case(name)
+    g = case["golden"]
+    dim = case["dim"]
+    da = dkt.DA(case["xyz"], case["lev"], dim, 1, case["max_depth"], ip0=g["ip0"], ip1=g["ip1"])
+    t = cases.oracle_tables_for(case)
+    u = cases.input_vector(da.n_nodes)
+    for K, alpha in ((dkt.operators.laplace_kref(dim, 1), dim - 2.0), (dkt.operators.mass_kref(dim, 1), float(dim))):
+        vo = flat.matvec(t, u, K, alpha=alpha, ip0=g["ip0"], ip1=g["ip1"])
+        op = dkt.Operator.dense(K, alpha)
+        v_fast = da.matvec(op, u)
+        v_dense = da.matvec(op, u, fastpath=False)
+        v_flat = da.matvec(op, u, flat=True)
+        for v in (v_fast, v_dense, v_flat):
+            assert np.abs(v - vo).max() <= TOL * np.abs(vo).max()
     da.close()
 
 
