@@ -188,7 +188,7 @@ def run_gpu(args):
                                "class B, max_level %d of max_depth %d" % (level, MAX_DEPTH),
                    "dim": DIM, "order": ORDER, "n_elem": da.n_elem, "n_nodes": n, "n_hanging_elem": da.n_hanging,
                    "tree_class": da.tree_class, "cache": "working set %.0f MB > 126 MB L2 (no flush needed)" % (da.alg_bytes / 1e6),
-                   "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3)},
+                   "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3), "chunks": da.chunk_info()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                      "alg_bytes_per_step": da.alg_bytes, "kernel": "whole matvec step (memset + regular + hanging kernels)"},

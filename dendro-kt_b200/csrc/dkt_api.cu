@@ -228,6 +228,17 @@ extern "C"
     CKA(cudaEventElapsedTime(ms, da->d.ev0, da->d.ev1));
     return DKT_OK;
   }
+  int dkt_da_chunk_info(const dkt_da *da, uint64_t out[10])
+  {
+    if (!da || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    const ChunkSet *cs[2] = {&da->d.reg, &da->d.hang};
+    for (int i = 0; i < 2; i++)
+    {
+      out[5 * i + 0] = cs[i]->nChunks; out[5 * i + 1] = cs[i]->elemsPerChunk; out[5 * i + 2] = cs[i]->maxNloc;
+      out[5 * i + 3] = cs[i]->maxLen; out[5 * i + 4] = cs[i]->totalNodes;
+    }
+    return DKT_OK;
+  }
   void *dkt_da_stream(dkt_da *da) { return da ? (void *)da->d.stream : nullptr; }
   int dkt_da_set_stream(dkt_da *da, void *cuda_stream)
   {

@@ -81,9 +81,10 @@ __global__ void k_ref_count(const uint32_t *ids, uint64_t n, uint32_t *cnt)
 // One CTA per chunk.  WRITE == false: only report the chunk's node count and longest run.
 template <bool WRITE>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, uint64_t elem0, uint64_t nSet, int N, int rows, int elemsPerChunk,
-              const uint32_t *refcnt, const uint8_t *isbdy, const uint64_t *node_off, int jdStride, uint32_t *nloc_out,
-              uint32_t *maxlen_out, uint32_t *slot, uint32_t *gid_out, uint16_t *meta_out, uint16_t *jd_out)
+k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz, const uint8_t *mv_lev, int dim, int max_depth,
+              int xorperm, uint64_t elem0, uint64_t nSet, int N, int rows, int elemsPerChunk, const uint32_t *refcnt,
+              const uint8_t *isbdy, const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out,
+              uint32_t *slot, uint32_t *gid_out, uint16_t *meta_out, uint16_t *jd_out)
 {
   using SortPairs = cub::BlockRadixSort<uint32_t, SORT_THREADS, SORT_ITEMS, uint16_t>;
   using SortKeys = cub::BlockRadixSort<uint32_t, SORT_THREADS, SORT_ITEMS>;
@@ -206,10 +207,15 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, uint64_t elem0, uint64
       s_jd[k] = above;  // #nodes with len > k
       above += s_hist[k];
     }
+    // diagonal k starts at a position congruent to k modulo 16 (the number of 8-byte bank pairs):
+    // the k-th contributions to one node - written by sibling elements in the same instruction
+    // under the XOR slot schedule - then fall into distinct banks
     int acc = 0;
     for (int k = 0; k <= ml; k++)
     {
       const int cnt = s_jd[k];
+      if (k < 16)
+        while ((acc & 15) != k) acc++;
       s_jd[k] = acc;
       acc += cnt;
     }
@@ -222,7 +228,20 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, uint64_t elem0, uint64
   for (int i = 0; i < SORT_ITEMS; i++)
   {
     const int posn = threadIdx.x * SORT_ITEMS + i;
-    const uint64_t dst = e0 * spe + (uint64_t)(val[i] % spe) * elemsPerChunk + val[i] / spe;  // rank-major inside the chunk
+    // rank-major inside the chunk; with the XOR schedule slot s of an element with Morton child
+    // number c holds lattice rank s ^ c (both rows), so that siblings touch the SAME node in the
+    // same instruction (shared-memory broadcast) - see k_mv3
+    int q = val[i] % spe;
+    const int el = val[i] / spe;
+    if (xorperm && val[i] < nslots)
+    {
+      const uint64_t ge = elem0 + e0 + el;
+      const int L = mv_lev[ge];
+      int cnum = 0;
+      for (int d = 0; d < dim; d++) cnum |= ((mv_xyz[ge * dim + d] >> (max_depth - L)) & 1u) << d;
+      q = (q < N) ? (q ^ cnum) : (N + ((q - N) ^ cnum));
+    }
+    const uint64_t dst = e0 * spe + (uint64_t)q * elemsPerChunk + el;
     if (key[i] == INVALID)
     {
       if (val[i] < nslots) slot[dst] = INVALID;
@@ -272,7 +291,10 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
   CK(cudaMalloc((void **)&mlen, (size_t)cs.nChunks * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&wide, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
   CK(cudaMalloc((void **)&off, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
-  k_chunk_build<false><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
+  const int xorperm = da.order == 1 ? 1 : 0;
+  cs.xorperm = xorperm;
+  k_chunk_build<false><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
+                                                                    xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
                                                                     da.d_node_isbdy, nullptr, 0, nloc, mlen, nullptr, nullptr, nullptr,
                                                                     nullptr);
   g_launches++;
@@ -301,7 +323,8 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
   CK(cudaMalloc((void **)&cs.d_gid, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&cs.d_meta, std::max<uint64_t>(total, 1) * sizeof(uint16_t)));
   CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * sizeof(uint16_t)));
-  k_chunk_build<true><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
+  k_chunk_build<true><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
+                                                                   xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
                                                                    da.d_node_isbdy, off, (int)cs.jdStride, nullptr, nullptr, cs.d_slot,
                                                                    cs.d_gid, cs.d_meta, cs.d_jd);
   g_launches++;
@@ -316,6 +339,8 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
 
 void free_chunks(DA &da)
 {
+  cudaFree(da.d_mv_child);
+  da.d_mv_child = nullptr;
   for (ChunkSet *cs : {&da.reg, &da.hang})
   {
     cudaFree(cs->d_slot); cudaFree(cs->d_gid); cudaFree(cs->d_meta); cudaFree(cs->d_jd); cudaFree(cs->d_node_off);
@@ -323,8 +348,22 @@ void free_chunks(DA &da)
   }
 }
 
+__global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_t n, int dim, int max_depth, uint8_t *child)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int L = lev[i];
+  int c = 0;
+  for (int d = 0; d < dim; d++) c |= ((xyz[i * dim + d] >> (max_depth - L)) & 1u) << d;
+  child[i] = (uint8_t)(L ? c : 0);
+}
+
 int build_chunks(DA &da)
 {
+  CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
+  k_child_numbers<<<(unsigned)((da.nMv + 255) / 256), 256, 0, da.stream>>>(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth,
+                                                                           da.d_mv_child);
+  g_launches++;
   uint32_t *refcnt = nullptr;
   CK(cudaMalloc((void **)&refcnt, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t)));
   CK(cudaMemsetAsync(refcnt, 0, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t), da.stream));
@@ -361,6 +400,7 @@ struct Mv3Params
   int q1mask;
   double lscale[32];
   double ip[2][M * M];
+  double ipx[2][M * M];  // ip[0] and J ip[1] J (XOR-permuted coordinates)
   double K[N * N];
 };
 
@@ -479,9 +519,32 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// undo the XOR slot schedule in registers: v[r] <- v[r ^ c]
+template <int DIM, int N, typename T>
+__device__ __forceinline__ void xor_unpermute(T *v, int c)
+{
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+  {
+    const bool f = (c >> d) & 1;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      if (i & (1 << d)) continue;
+      const T a = v[i], b = v[i | (1 << d)];
+      v[i] = f ? b : a;
+      v[i | (1 << d)] = f ? a : b;
+    }
+  }
+}
+
 // TPB threads, one element per thread, NPT nodes per thread (chunk nodes <= NPT*TPB).
+// Order 1: slot s of an element with child number c holds rank s ^ c.  The identity and
+// Walsh-Hadamard operators commute with that permutation (H D H is a convolution on Z_2^dim) and
+// the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
+// work in permuted coordinates throughout; the dense path un-permutes the slot words first.
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT>
-__global__ void __launch_bounds__(TPB, ((HANG && Mv3Params<DIM, ORDER>::N <= 16) ? 3 : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
+__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? 4 : 3) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int M = ORDER + 1;
@@ -534,9 +597,15 @@ __global__ void __launch_bounds__(TPB, ((HANG && Mv3Params<DIM, ORDER>::N <= 16)
 #pragma unroll
       for (int r = 0; r < ROWS * N; r++) w[r] = sw[(uint32_t)r * E];
       lev = p.lev[e0 + tid];
-      if (HANG) child = p.child[e0 + tid];
+      if (HANG || (ORDER == 1 && OPKIND == DKT_OP_DENSE)) child = p.child[e0 + tid];
+      if (ORDER == 1 && OPKIND == DKT_OP_DENSE)
+      {  // natural rank order for the dense product
+        xor_unpermute<DIM, N, uint32_t>(w, child);
+        if (HANG) xor_unpermute<DIM, N, uint32_t>(w + N, child);
+      }
     }
   };
+  constexpr bool PERM = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
 
   // ---- prologue: everything for the first chunk ------------------------------------------------
   uint64_t offA = p.node_off[c], offB = p.node_off[c + 1];
@@ -610,7 +679,7 @@ __global__ void __launch_bounds__(TPB, ((HANG && Mv3Params<DIM, ORDER>::N <= 16)
           double ein[N], eout[N], par[N];
 #pragma unroll
           for (int r = 0; r < N; r++) par[r] = (w[N + r] == INVALID) ? 0.0 : un[w[N + r] & 0xFFFFu];
-          tensor_interp3<DIM, M, false>(p.ip, child, par);
+          tensor_interp3<DIM, M, false>(PERM ? p.ipx : p.ip, child, par);
 #pragma unroll
           for (int r = 0; r < N; r++) ein[r] = (w[r] == INVALID) ? par[r] : un[w[r] & 0xFFFFu];
           apply_op3<DIM, ORDER, OPKIND>(p, lev, ein, eout);
@@ -623,7 +692,7 @@ __global__ void __launch_bounds__(TPB, ((HANG && Mv3Params<DIM, ORDER>::N <= 16)
               eout[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
             }
           }
-          tensor_interp3<DIM, M, true>(p.ip, child, eout);
+          tensor_interp3<DIM, M, true>(PERM ? p.ipx : p.ip, child, eout);
 #pragma unroll
           for (int q = 0; q < N; q++)
           {
@@ -674,7 +743,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   p.slot = cs.d_slot; p.gid = cs.d_gid; p.meta = cs.d_meta; p.jd = cs.d_jd; p.node_off = cs.d_node_off;
   p.lev = lev; p.child = child; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
-  p.xcap = (uint32_t)rows_per_chunk(N) * N;
+  p.xcap = (uint32_t)rows_per_chunk(N) * N + 256u;  // + padding of the first 16 diagonals
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
   const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.jdStride * sizeof(int);
@@ -698,14 +767,14 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p)
   int rc = DKT_OK;
   if (da.reg.nChunks)
   {
-    if (da.reg.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6>(da, da.reg, p, da.d_mv_lev, nullptr);
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16>(da, da.reg, p, da.d_mv_lev, nullptr);
+    if (da.reg.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
     if (rc) return rc;
   }
   if (da.hang.nChunks)
   {
-    if (da.hang.maxNloc <= 8u * TPB_H) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_child);
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_child);
+    if (da.hang.maxNloc <= 8u * TPB_H) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
     if (rc) return rc;
   }
   CK(cudaGetLastError());
@@ -723,6 +792,12 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
   for (int l = 0; l < 32; l++) p.lscale[l] = scale * std::pow(2.0, -op->alpha * l);
   for (int b = 0; b < 2; b++)
     for (int i = 0; i < P::M * P::M; i++) p.ip[b][i] = da.ip[b][i];
+  for (int k = 0; k < P::M; k++)
+    for (int j = 0; j < P::M; j++)
+    {
+      p.ipx[0][k * P::M + j] = da.ip[0][k * P::M + j];
+      p.ipx[1][k * P::M + j] = da.ip[1][(P::M - 1 - k) * P::M + (P::M - 1 - j)];
+    }
   bool hadamard = false;
   if (op->kind == DKT_OP_DENSE)
   {

@@ -35,6 +35,7 @@ extern uint64_t g_launches;
 struct ChunkSet
 {
   int rows = 1;                  // slot rows per element: 1 regular, 2 hanging (own + parent lattice)
+  int xorperm = 0;               // slot s of an element with child number c holds rank s ^ c (order 1)
   uint64_t nElem = 0;
   uint32_t nChunks = 0, elemsPerChunk = 0, maxNloc = 0, maxLen = 0, jdStride = 0;
   uint64_t totalNodes = 0;
@@ -72,6 +73,7 @@ struct DA
   uint32_t *d_mv_src = nullptr;    // [nMv] position in SFC visit order (for export)
   uint32_t *d_pnode = nullptr;     // [nHang*N]
   uint8_t *d_child = nullptr;      // [nHang]
+  uint8_t *d_mv_child = nullptr;   // [nMv] Morton child number of every visited element
 
   // coordinate -> node lookup: sorted unique packed keys of all lattice locations
   uint64_t *d_ukey = nullptr;      // [nU]
