@@ -39,6 +39,7 @@ using namespace dkt;
 struct dkt_da
 {
   DA d;
+  Dist dist;
 };
 
 #define CKA(call)                                                                                 \
@@ -77,9 +78,29 @@ extern "C"
     return t.nrot;
   }
 
+  int dkt_nccl_unique_id(void *out128)
+  {
+    if (!out128) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    return nccl_unique_id(out128);
+  }
   int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
                     uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out)
   {
+    return dkt_da_create_dist(dim, order, max_depth, sfc_mode, elem_xyz, elem_lev, n_elem, ip0, ip1, flags, 0, 1, nullptr, out);
+  }
+  int dkt_da_export_owned_ids(const dkt_da *da, uint32_t *ids)
+  {
+    if (!da || !ids) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    if (!da->dist.active) { set_error("not a partitioned DA"); return DKT_ERR_INVALID; }
+    CKA(cudaSetDevice(da->d.device));
+    if (da->dist.nOwned) CKA(cudaMemcpy(ids, da->dist.d_owned_gid, da->dist.nOwned * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return DKT_OK;
+  }
+  int dkt_da_create_dist(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
+                         uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, int rank, int nranks,
+                         const void *nccl_id, dkt_da **out)
+  {
+    if (nranks > 1 && !nccl_id) { set_error("nccl_id is NULL"); return DKT_ERR_INVALID; }
     if (!out) { set_error("out is NULL"); return DKT_ERR_INVALID; }
     *out = nullptr;
     if (dim < 2 || dim > 4) { set_error("dim must be 2, 3 or 4"); return DKT_ERR_INVALID; }
@@ -110,10 +131,12 @@ extern "C"
     else
       exact_interp(order, d.ip);
     int rc = build_da(d, elem_xyz, elem_lev, n_elem, flags);
+    if (rc == DKT_OK && nranks > 1) rc = partition_da(d, h->dist, rank, nranks, nccl_id);
     if (rc == DKT_OK) rc = build_chunks(d);
     if (rc != DKT_OK)
     {
       const std::string keep = g_err;
+      free_dist(h->dist);
       free_da(d);
       delete h;
       g_err = keep;
@@ -127,6 +150,7 @@ extern "C"
   {
     if (!da) return DKT_OK;
     cudaSetDevice(da->d.device);
+    free_dist(da->dist);
     free_da(da->d);
     delete da;
     return DKT_OK;
@@ -137,11 +161,19 @@ extern "C"
     if (!da || !s) { set_error("NULL argument"); return DKT_ERR_INVALID; }
     const DA &d = da->d;
     std::memset(s, 0, sizeof(*s));
-    s->n_elem = d.nElem; s->n_mv_elem = d.nMv; s->n_nodes = d.nNodes; s->n_boundary = d.nBdy; s->n_hanging = d.nHang;
+    const Dist &ds = da->dist;
+    s->n_elem = d.nElem; s->n_mv_elem = d.nMv; s->n_nodes = ds.active ? ds.nOwned : d.nNodes; s->n_boundary = d.nBdy;
+    s->n_hanging = d.nHang;
     s->n_split = d.nSplit; s->nodes_per_elem = d.N; s->tree_class = d.tree_class; s->finest_level = d.finest_level;
+    s->n_ranks = ds.active ? ds.nranks : 1;
+    s->n_global_nodes = ds.active ? ds.nGlobalNodes : d.nNodes;
+    s->n_ghost_nodes = ds.active ? ds.nGhost : 0;
+    s->n_global_elem = d.nElem;
     // read u + write v, the uint32 element->node table, and per hanging element
     // the parent-cell node ids + child number/masks
-    s->alg_bytes = d.nNodes * 16ull + d.nMv * (uint64_t)d.N * 4ull + d.nHang * ((uint64_t)d.N * 4ull + 8ull);
+    // (+ 16 B per ghost node when partitioned: 8 B each way, send + receive)
+    s->alg_bytes = s->n_nodes * 16ull + d.nMv * (uint64_t)d.N * 4ull + d.nHang * ((uint64_t)d.N * 4ull + 8ull) +
+                   s->n_ghost_nodes * 16ull;
     return DKT_OK;
   }
 
@@ -154,6 +186,7 @@ extern "C"
   int dkt_da_export_elements(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
     const DA &d = da->d;
     CKA(cudaSetDevice(d.device));
     D2H(xyz, d.d_elem_xyz, d.nElem * d.dim * sizeof(uint32_t));
@@ -163,6 +196,7 @@ extern "C"
   int dkt_da_export_nodes(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
     const DA &d = da->d;
     CKA(cudaSetDevice(d.device));
     D2H(xyz, d.d_node_xyz, d.nNodes * d.dim * sizeof(uint32_t));
@@ -172,6 +206,7 @@ extern "C"
   int dkt_da_export_boundary(const dkt_da *da, uint32_t *ids)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
     const DA &d = da->d;
     CKA(cudaSetDevice(d.device));
     D2H(ids, d.d_bdy, d.nBdy * sizeof(uint32_t));
@@ -180,6 +215,7 @@ extern "C"
   int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, uint32_t *e2n, uint32_t *pnode, uint8_t *child)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
+    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
     const DA &d = da->d;
     CKA(cudaSetDevice(d.device));
     D2H(mv_xyz, d.d_mv_xyz, d.nMv * d.dim * sizeof(uint32_t));
@@ -195,7 +231,7 @@ extern "C"
     if (!da || !op || !in || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
     DA &d = da->d;
     CKA(cudaSetDevice(d.device));
-    const size_t bytes = d.nNodes * sizeof(double);
+    const size_t bytes = (da->dist.active ? da->dist.nOwned : d.nNodes) * sizeof(double);
     const double *din = in;
     double *dout = out;
     if (!(flags & DKT_VEC_DEVICE))
@@ -210,7 +246,9 @@ extern "C"
       dout = d.d_out;
     }
     CKA(cudaEventRecord(d.ev0, d.stream));
-    const int rc = (flags & DKT_MV_FLAT) ? run_matvec(d, op, din, dout, scale, flags) : run_matvec_chunked(d, op, din, dout, scale, flags);
+    const int rc = da->dist.active ? run_matvec_dist(d, da->dist, op, din, dout, scale, flags)
+                   : (flags & DKT_MV_FLAT) ? run_matvec(d, op, din, dout, scale, flags)
+                                           : run_matvec_chunked(d, op, din, dout, scale, flags);
     if (rc != DKT_OK) return rc;
     CKA(cudaEventRecord(d.ev1, d.stream));
     if (!(flags & DKT_VEC_DEVICE))

@@ -1,0 +1,422 @@
+// Multi-GPU matvec: SFC-contiguous element ranges per rank + NCCL ghost exchange.
+//
+// Replaces the reference's distributed DA for the matvec path:
+//   * partition ............ SFC_Tree::distTreePartition (src/tsort.cpp:229-508): contiguous ranges
+//                            of the tree order, equal element counts
+//   * node ownership ....... the rank of the first (lowest tree position) element touching the node
+//                            (the reference: owner of the node's SFC key, include/nsort.tcc:715-786)
+//   * ghosted vector ....... [owned | ghosts grouped by owner rank]  (reference: [pre | local | post],
+//                            src/oda.cpp:115-121)
+//   * readFromGhostBegin/End (include/oda.tcc:212-315): owners send the values other ranks ghost
+//   * writeToGhostsBegin/End (include/oda.tcc:319-435): ghost partial sums go back and are added
+// as ncclSend/ncclRecv groups over NVLink on the DA's stream.
+//
+// Round-1 construction strategy ("replicated build, partitioned matvec"): every rank builds the
+// GLOBAL tables on its own GPU with the single-rank pipeline (dkt_build.cu) - identical on all
+// ranks, so ownership and both sides of every send/recv list are derived without communication -
+// then keeps only its element range, renumbers the nodes it touches and builds its chunk tables.
+// The global tables are freed afterwards.  (A build whose memory scales with the local part only
+// is future work; the matvec itself is fully partitioned.)
+#include "dkt_internal.h"
+
+#include <cub/cub.cuh>
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace dkt
+{
+#define CK(call)                                                                                     \
+  do                                                                                                 \
+  {                                                                                                  \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+    {                                                                                                \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return DKT_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+// ---- NCCL, resolved at run time (libnccl.so.2 ships with torch; no link-time dependency) ----------
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_p;
+struct NcclApi
+{
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_p) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;
+
+static int load_nccl()
+{
+  if (g_nccl.lib) return DKT_OK;
+  const char *cands[] = {getenv("DKT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char *c : cands)
+  {
+    if (!c) continue;
+    g_nccl.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) { set_error(std::string("cannot load libnccl.so.2 (set DKT_NCCL_LIB): ") + dlerror()); return DKT_ERR_NCCL; }
+#define SYM(field, name)                                                       \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                         \
+  if (!g_nccl.field) { set_error(std::string("libnccl lacks ") + name); return DKT_ERR_NCCL; }
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return DKT_OK;
+}
+#define NCK(call)                                                                        \
+  do                                                                                     \
+  {                                                                                      \
+    int r_ = (call);                                                                     \
+    if (r_ != 0)                                                                         \
+    {                                                                                    \
+      set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r_));                  \
+      return DKT_ERR_NCCL;                                                               \
+    }                                                                                    \
+  } while (0)
+
+int nccl_unique_id(void *out128)
+{
+  int rc = load_nccl();
+  if (rc) return rc;
+  NCK(g_nccl.GetUniqueId((ncclUniqueId_t *)out128));
+  return DKT_OK;
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+struct Bounds
+{
+  uint32_t b[66];  // b[p] = first tree position of rank p, b[nranks] = nMv
+  int nranks;
+};
+__device__ __forceinline__ int rank_of(uint32_t src, const Bounds &B)
+{
+  int p = 0;
+  while (p + 1 < B.nranks && src >= B.b[p + 1]) p++;
+  return p;
+}
+
+// per node: smallest tree position of a referencing element, and the set of ranks referencing it
+__global__ void k_node_refs(const uint32_t *ids, uint64_t n, int N, const uint32_t *src, uint64_t elem0, Bounds B, uint32_t *minsrc,
+                            unsigned long long *refmask)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t node = ids[i];
+  if (node == INVALID) return;
+  const uint32_t s = src[elem0 + i / N];
+  atomicMin(minsrc + node, s);
+  atomicOr(refmask + node, 1ull << rank_of(s, B));
+}
+
+// flags for one selection pass: mode 0 = owned by me; 1 = my ghost owned by peer; 2 = owned by me and
+// referenced by peer (send list)
+__global__ void k_select(const uint32_t *minsrc, const unsigned long long *refmask, uint64_t n, Bounds B, int me, int peer, int mode,
+                         uint8_t *flag)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int owner = rank_of(minsrc[i], B);
+  bool f;
+  if (mode == 0) f = owner == me;
+  else if (mode == 1) f = owner == peer && ((refmask[i] >> me) & 1ull);
+  else f = owner == me && ((refmask[i] >> peer) & 1ull);
+  flag[i] = f ? 1 : 0;
+}
+__global__ void k_assign_local(const uint8_t *flag, const uint64_t *pos, uint64_t n, uint32_t base, uint32_t *g2l, uint32_t *l2g)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const uint32_t l = base + (uint32_t)pos[i];
+  g2l[i] = l;
+  l2g[l] = (uint32_t)i;
+}
+__global__ void k_send_list(const uint8_t *flag, const uint64_t *pos, uint64_t n, const uint32_t *g2l, uint32_t *out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[pos[i]] = g2l[i];
+}
+__global__ void k_u8_widen(const uint8_t *in, uint64_t n, uint64_t *out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void k_remap(const uint32_t *in, uint64_t n, const uint32_t *g2l, uint32_t *out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = in[i];
+  out[i] = v == INVALID ? INVALID : g2l[v];
+}
+__global__ void k_gather_u8(const uint8_t *in, const uint32_t *idx, uint64_t n, uint8_t *out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+__global__ void k_lower_bound(const uint32_t *a, uint64_t n, uint32_t key, uint64_t *out)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  *out = lo;
+}
+__global__ void k_pack(const double *v, const uint32_t *idx, uint64_t n, double *buf)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = v[idx[i]];
+}
+// several peers may return contributions to the same owned node -> atomic
+__global__ void k_unpack_add(double *v, const uint32_t *idx, uint64_t n, const double *buf)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(v + idx[i], buf[i]);
+}
+
+#define LAUNCHS(kern, n, stream, ...)                                          \
+  do                                                                           \
+  {                                                                            \
+    if ((n) > 0)                                                               \
+    {                                                                          \
+      kern<<<(unsigned)(((n) + 255) / 256), 256, 0, stream>>>(__VA_ARGS__);     \
+      g_launches++;                                                            \
+    }                                                                          \
+  } while (0)
+
+// exclusive positions of set flags + total (host)
+static int positions(DA &g, const uint8_t *flag, uint64_t n, uint64_t *wide, uint64_t *pos, uint64_t &total)
+{
+  total = 0;
+  if (n == 0) return DKT_OK;
+  CK(cudaMemsetAsync(wide + n, 0, sizeof(uint64_t), g.stream));
+  LAUNCHS(k_u8_widen, n, g.stream, flag, n, wide);
+  int rc = device_exclusive_scan(g, wide, pos, n + 1);
+  if (rc) return rc;
+  CK(cudaMemcpy(&total, pos + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DKT_OK;
+}
+
+void free_dist(Dist &d)
+{
+  if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)d.comm);
+  cudaFree(d.d_send_idx); cudaFree(d.d_send_buf); cudaFree(d.d_recv_buf); cudaFree(d.d_in_local); cudaFree(d.d_out_local);
+  cudaFree(d.d_owned_gid);
+  d = Dist();
+}
+
+// g: the global single-rank DA (already built, no chunk tables).  On success `g` has been turned into
+// the LOCAL DA of this rank (its global tables released) and `dist` describes the exchange.
+int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
+{
+  if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) { set_error("bad rank/nranks (1..64)"); return DKT_ERR_INVALID; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  dist.rank = rank;
+  dist.nranks = nranks;
+  const int N = g.N, dim = g.dim;
+  const uint64_t nMv = g.nMv, nReg = g.nReg, nHang = g.nHang, nNodes = g.nNodes;
+  dist.nGlobalNodes = nNodes;
+  dist.nGlobalElems = g.nElem;
+  Bounds B;
+  B.nranks = nranks;
+  for (int p = 0; p <= nranks; p++) B.b[p] = (uint32_t)((nMv * (uint64_t)p) / (uint64_t)nranks);
+
+  // ---- ownership and reference masks ------------------------------------------------------------------
+  uint32_t *minsrc = nullptr;
+  unsigned long long *refmask = nullptr;
+  CK(cudaMalloc((void **)&minsrc, std::max<uint64_t>(nNodes, 1) * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&refmask, std::max<uint64_t>(nNodes, 1) * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(minsrc, 0xFF, nNodes * sizeof(uint32_t), g.stream));
+  CK(cudaMemsetAsync(refmask, 0, nNodes * sizeof(unsigned long long), g.stream));
+  LAUNCHS(k_node_refs, nMv * N, g.stream, g.d_e2n, nMv * N, N, g.d_mv_src, 0, B, minsrc, refmask);
+  LAUNCHS(k_node_refs, nHang * N, g.stream, g.d_pnode, nHang * N, N, g.d_mv_src, nReg, B, minsrc, refmask);
+
+  // ---- local numbering: [owned (global order) | ghosts by owner rank (global order inside)] -----------
+  uint8_t *flag = nullptr;
+  uint64_t *wide = nullptr, *pos = nullptr;
+  uint32_t *g2l = nullptr, *l2g = nullptr;
+  CK(cudaMalloc((void **)&flag, std::max<uint64_t>(nNodes, 1)));
+  CK(cudaMalloc((void **)&wide, (nNodes + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&pos, (nNodes + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&g2l, std::max<uint64_t>(nNodes, 1) * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&l2g, std::max<uint64_t>(nNodes, 1) * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(g2l, 0xFF, nNodes * sizeof(uint32_t), g.stream));
+  uint64_t nOwned = 0;
+  LAUNCHS(k_select, nNodes, g.stream, minsrc, refmask, nNodes, B, rank, rank, 0, flag);
+  rc = positions(g, flag, nNodes, wide, pos, nOwned);
+  if (rc) return rc;
+  LAUNCHS(k_assign_local, nNodes, g.stream, flag, pos, nNodes, 0u, g2l, l2g);
+  dist.nOwned = nOwned;
+  dist.recv_off.assign(nranks + 1, 0);
+  dist.send_off.assign(nranks + 1, 0);
+  uint64_t nLocal = nOwned;
+  for (int p = 0; p < nranks; p++)
+  {
+    dist.recv_off[p] = nLocal - nOwned;
+    if (p == rank) continue;
+    uint64_t cnt = 0;
+    LAUNCHS(k_select, nNodes, g.stream, minsrc, refmask, nNodes, B, rank, p, 1, flag);
+    rc = positions(g, flag, nNodes, wide, pos, cnt);
+    if (rc) return rc;
+    LAUNCHS(k_assign_local, nNodes, g.stream, flag, pos, nNodes, (uint32_t)nLocal, g2l, l2g);
+    nLocal += cnt;
+  }
+  dist.recv_off[nranks] = nLocal - nOwned;
+  dist.nGhost = nLocal - nOwned;
+  // ---- send lists ------------------------------------------------------------------------------------------
+  std::vector<uint64_t> scnt(nranks, 0);
+  uint64_t totalSend = 0;
+  for (int p = 0; p < nranks; p++)
+  {
+    if (p == rank) continue;
+    LAUNCHS(k_select, nNodes, g.stream, minsrc, refmask, nNodes, B, rank, p, 2, flag);
+    rc = positions(g, flag, nNodes, wide, pos, scnt[p]);
+    if (rc) return rc;
+    totalSend += scnt[p];
+  }
+  CK(cudaMalloc((void **)&dist.d_send_idx, std::max<uint64_t>(totalSend, 1) * sizeof(uint32_t)));
+  {
+    uint64_t off = 0;
+    for (int p = 0; p < nranks; p++)
+    {
+      dist.send_off[p] = off;
+      if (p == rank || scnt[p] == 0) continue;
+      uint64_t c2 = 0;
+      LAUNCHS(k_select, nNodes, g.stream, minsrc, refmask, nNodes, B, rank, p, 2, flag);
+      rc = positions(g, flag, nNodes, wide, pos, c2);
+      if (rc) return rc;
+      LAUNCHS(k_send_list, nNodes, g.stream, flag, pos, nNodes, g2l, dist.d_send_idx + off);
+      off += scnt[p];
+    }
+    dist.send_off[nranks] = off;
+  }
+  CK(cudaMalloc((void **)&dist.d_send_buf, std::max<uint64_t>(totalSend, 1) * sizeof(double)));
+  CK(cudaMalloc((void **)&dist.d_recv_buf, std::max<uint64_t>(totalSend, 1) * sizeof(double)));
+  CK(cudaMalloc((void **)&dist.d_in_local, std::max<uint64_t>(nLocal, 1) * sizeof(double)));
+  CK(cudaMalloc((void **)&dist.d_out_local, std::max<uint64_t>(nLocal, 1) * sizeof(double)));
+  CK(cudaMalloc((void **)&dist.d_owned_gid, std::max<uint64_t>(nOwned, 1) * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(dist.d_owned_gid, l2g, nOwned * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+
+  // ---- my element ranges (regular and hanging lists are each sorted by tree position) ----------------------
+  uint64_t *dlb = nullptr, lb[4];
+  CK(cudaMalloc((void **)&dlb, 4 * sizeof(uint64_t)));
+  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src, nReg, B.b[rank], dlb + 0);
+  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src, nReg, B.b[rank + 1], dlb + 1);
+  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src + nReg, nHang, B.b[rank], dlb + 2);
+  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src + nReg, nHang, B.b[rank + 1], dlb + 3);
+  g_launches += 4;
+  CK(cudaMemcpyAsync(lb, dlb, sizeof(lb), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  cudaFree(dlb);
+  const uint64_t r0 = lb[0], r1 = lb[1], h0 = lb[2], h1 = lb[3];
+  const uint64_t nRegL = r1 - r0, nHangL = h1 - h0, nMvL = nRegL + nHangL;
+
+  // ---- local tables ---------------------------------------------------------------------------------------------
+  uint32_t *e2nL = nullptr, *pnodeL = nullptr, *xyzL = nullptr, *srcL = nullptr;
+  uint8_t *levL = nullptr, *childL = nullptr, *bdyL = nullptr;
+  CK(cudaMalloc((void **)&e2nL, std::max<uint64_t>(nMvL, 1) * N * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&pnodeL, std::max<uint64_t>(nHangL, 1) * N * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&xyzL, std::max<uint64_t>(nMvL, 1) * dim * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&srcL, std::max<uint64_t>(nMvL, 1) * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&levL, std::max<uint64_t>(nMvL, 1)));
+  CK(cudaMalloc((void **)&childL, std::max<uint64_t>(nHangL, 1)));
+  CK(cudaMalloc((void **)&bdyL, std::max<uint64_t>(nLocal, 1)));
+  LAUNCHS(k_remap, nRegL * N, g.stream, g.d_e2n + r0 * N, nRegL * N, g2l, e2nL);
+  LAUNCHS(k_remap, nHangL * N, g.stream, g.d_e2n + (nReg + h0) * N, nHangL * N, g2l, e2nL + nRegL * N);
+  LAUNCHS(k_remap, nHangL * N, g.stream, g.d_pnode + h0 * N, nHangL * N, g2l, pnodeL);
+  CK(cudaMemcpyAsync(xyzL, g.d_mv_xyz + r0 * dim, nRegL * dim * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(xyzL + nRegL * dim, g.d_mv_xyz + (nReg + h0) * dim, nHangL * dim * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(levL, g.d_mv_lev + r0, nRegL, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(levL + nRegL, g.d_mv_lev + nReg + h0, nHangL, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(srcL, g.d_mv_src + r0, nRegL * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(srcL + nRegL, g.d_mv_src + nReg + h0, nHangL * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(childL, g.d_child + h0, nHangL, cudaMemcpyDeviceToDevice, g.stream));
+  LAUNCHS(k_gather_u8, nLocal, g.stream, g.d_node_isbdy, l2g, nLocal, bdyL);
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+
+  // ---- swap the global tables for the local ones -------------------------------------------------------------------
+  cudaFree(g.d_e2n); cudaFree(g.d_pnode); cudaFree(g.d_mv_xyz); cudaFree(g.d_mv_src); cudaFree(g.d_mv_lev); cudaFree(g.d_child);
+  cudaFree(g.d_node_isbdy); cudaFree(g.d_ukey); cudaFree(g.d_unode);
+  g.d_ukey = nullptr; g.d_unode = nullptr;
+  g.d_e2n = e2nL; g.d_pnode = pnodeL; g.d_mv_xyz = xyzL; g.d_mv_src = srcL; g.d_mv_lev = levL; g.d_child = childL;
+  g.d_node_isbdy = bdyL;
+  g.nMv = nMvL; g.nReg = nRegL; g.nHang = nHangL;
+  g.nNodes = nLocal;  // the chunk tables and the kernels work on the local (owned + ghost) vector
+  cudaFree(minsrc); cudaFree(refmask); cudaFree(flag); cudaFree(wide); cudaFree(pos); cudaFree(g2l); cudaFree(l2g);
+
+  // ---- communicator ------------------------------------------------------------------------------------------------------
+  if (nranks > 1)
+  {
+    ncclUniqueId_t id;
+    std::memcpy(&id, nccl_id, sizeof(id));
+    ncclComm_p comm = nullptr;
+    NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    dist.comm = comm;
+  }
+  dist.active = true;
+  return DKT_OK;
+}
+
+// v = A u on the partition: in/out are DEVICE vectors of the nOwned owned nodes
+int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
+{
+  cudaStream_t s = da.stream;
+  const uint64_t nOwned = d.nOwned;
+  const uint64_t totalSend = d.send_off[d.nranks];
+  CK(cudaMemcpyAsync(d.d_in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (d.nranks > 1)
+  {
+    // readFromGhost: owners -> ghosts, received straight into the ghost segments of the local vector
+    LAUNCHS(k_pack, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_buf);
+    NCK(g_nccl.GroupStart());
+    for (int p = 0; p < d.nranks; p++)
+    {
+      if (p == d.rank) continue;
+      const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
+      if (sc) NCK(g_nccl.Send(d.d_send_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (rcv) NCK(g_nccl.Recv(d.d_in_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+    }
+    NCK(g_nccl.GroupEnd());
+    g_launches++;
+  }
+  int rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, d.d_in_local, d.d_out_local, scale, flags)
+                                 : run_matvec_chunked(da, op, d.d_in_local, d.d_out_local, scale, flags);
+  if (rc) return rc;
+  if (d.nranks > 1)
+  {
+    // writeToGhosts: ghost partial sums -> owners, accumulated
+    NCK(g_nccl.GroupStart());
+    for (int p = 0; p < d.nranks; p++)
+    {
+      if (p == d.rank) continue;
+      const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
+      if (rcv) NCK(g_nccl.Send(d.d_out_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (sc) NCK(g_nccl.Recv(d.d_recv_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+    }
+    NCK(g_nccl.GroupEnd());
+    g_launches++;
+    LAUNCHS(k_unpack_add, totalSend, s, d.d_out_local, d.d_send_idx, totalSend, d.d_recv_buf);
+  }
+  CK(cudaMemcpyAsync(d_out, d.d_out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return DKT_OK;
+}
+} // namespace dkt

@@ -90,6 +90,24 @@ struct DA
   float last_ms = 0.f;
 };
 
+// Exchange plan of one rank of a partitioned DA (dkt_dist.cu).
+struct Dist
+{
+  bool active = false;
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;                 // ncclComm_t
+  uint64_t nOwned = 0, nGhost = 0, nGlobalNodes = 0, nGlobalElems = 0;
+  std::vector<uint64_t> send_off, recv_off;  // [nranks+1] offsets into the send list / the ghost segment
+  uint32_t *d_send_idx = nullptr;       // local ids of owned nodes other ranks ghost, grouped by peer
+  double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+  double *d_in_local = nullptr, *d_out_local = nullptr;  // [owned | ghosts by owner rank]
+  uint32_t *d_owned_gid = nullptr;      // global (single-rank DA order) id of each owned node
+};
+int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id);
+int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+void free_dist(Dist &d);
+int nccl_unique_id(void *out128);
+
 int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t n, unsigned flags);
 void free_da(DA &da);
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);

@@ -80,7 +80,10 @@ typedef struct dkt_sizes
   int nodes_per_elem;    /* (order+1)^dim                                                    */
   int tree_class;        /* DKT_CLASS_*                                                      */
   int finest_level;
-  int reserved;
+  int n_ranks;           /* 1 for a single-rank DA                                           */
+  uint64_t n_global_nodes; /* partitioned DA: CG nodes of the whole tree (n_nodes = owned ones) */
+  uint64_t n_ghost_nodes;  /* partitioned DA: nodes this rank touches but does not own          */
+  uint64_t n_global_elem;
 } dkt_sizes;
 
 const char *dkt_last_error(void);
@@ -103,6 +106,20 @@ int dkt_sfc_tables(int dim, int sfc_mode, char *rotations, int *hilbert_table);
 int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
                   uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out);
 int dkt_da_destroy(dkt_da *da);
+
+/* Multi-GPU, one process per GPU.  Replaces the distributed DA of the reference for the matvec
+ * path: SFC-contiguous element ranges (SFC_Tree::distTreePartition, src/tsort.cpp:229-508), node
+ * ownership, and the ghost exchange readFromGhostBegin/End + writeToGhostsBegin/End
+ * (include/oda.tcc:212-435) as ncclSend/ncclRecv groups.  Every rank passes the SAME full tree;
+ * rank r keeps elements [r*n/R, (r+1)*n/R) of the tree order.  nccl_id: 128 bytes from
+ * dkt_nccl_unique_id() on rank 0, broadcast by the caller (MPI, torch.distributed, a file ...).
+ * Vectors passed to dkt_matvec then hold this rank's OWNED nodes (dkt_sizes.n_nodes of them);
+ * dkt_da_export_owned_ids gives their index in the single-rank DA order. */
+int dkt_nccl_unique_id(void *out128);
+int dkt_da_create_dist(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
+                       uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, int rank, int nranks,
+                       const void *nccl_id, dkt_da **out);
+int dkt_da_export_owned_ids(const dkt_da *da, uint32_t *ids);
 
 int dkt_da_sizes(const dkt_da *da, dkt_sizes *out);
 /* tree in DA order: what DA::getTreePartFront()/Back() bracket (include/oda.h:255-258) */
