@@ -103,6 +103,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def weak_window(n_gpus, per_gpu_elems):
+    """Time window of the moving ball such that the level-9 tree has ~per_gpu_elems * n_gpus
+    elements (measured: elements ~= 9.4e6 + 3.41e8 * width at max_level 9)."""
+    w = (n_gpus * per_gpu_elems - 9.4e6) / 3.41e8
+    return min(max(w, 1.0 / 512), 0.5)
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -115,51 +122,80 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
     torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        raise SystemExit("multi-GPU partitioning is not implemented yet in this revision")
 
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t)
+
+    # ---- the tree: identical on every rank (weak scaling: the ball's time window grows with N) ----
     level = args.level
+    width = weak_window(world, args.per_gpu_elems) if level == 9 else 0.5
     t0 = time.time()
-    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH, use_torch=True)
+    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH, use_torch=True, t0=0.5 - width / 2, t1=0.5 + width / 2)
     torch.cuda.synchronize()
     t_tree = time.time() - t0
     t0 = time.time()
-    da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(dkt.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes())
+    else:
+        da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH)
     t_build = time.time() - t0
+    n_elem_global = int(lev.numel())
     del xyz, lev
     torch.cuda.empty_cache()
     K = operators.laplace_kref(DIM, ORDER)
     op = dkt.Operator.dense(K, alpha=DIM - 2.0)
-    n = da.n_nodes
+    n = da.n_nodes                      # owned by this rank
+    n_global = da.n_global_nodes
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     da.set_stream(stream.cuda_stream)
-    g = torch.Generator(device="cuda").manual_seed(99)
+    g = torch.Generator(device="cuda").manual_seed(99 + rank)
     u = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
     v = torch.empty_like(u)
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
     for _ in range(args.warmup):
         da.matvec(op, u, v)
-    torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = dkt.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    torch.cuda.synchronize()
+    barrier()
     ev[0].record(stream)
     for i in range(args.steps):
         da.matvec(op, u, v)
         ev[i + 1].record(stream)
-    torch.cuda.synchronize()
+    barrier()
     launches = dkt.kernel_launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     ms = total_ms / args.steps
-    value = n / (ms * 1e-3)
+    value = n_global / (ms * 1e-3)
 
     # ---- end to end through the host API: pinned host buffers, H2D + matvec + D2H every step ----
     uh = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -168,44 +204,57 @@ def run_gpu(args):
     un, vn = uh.numpy(), vh.numpy()
     for _ in range(min(args.warmup, 3)):
         da.matvec(op, un, vn)
-    torch.cuda.synchronize()
     e2e_steps = max(3, min(args.steps, 10))
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         da.matvec(op, un, vn)  # synchronous: returns after the D2H copy has landed
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     check = float(np.abs(vn - v.cpu().numpy()).max() / max(np.abs(vn).max(), 1e-300))
 
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
-    achieved = da.alg_bytes / (ms * 1e-3) / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "4D p=1 Laplacian matvec (dense 16x16 K_e = h^2 K_ref), space-time moving-ball adaptive tree, "
-                               "class B, max_level %d of max_depth %d" % (level, MAX_DEPTH),
-                   "dim": DIM, "order": ORDER, "n_elem": da.n_elem, "n_nodes": n, "n_hanging_elem": da.n_hanging,
-                   "tree_class": da.tree_class, "cache": "working set %.0f MB > 126 MB L2 (no flush needed)" % (da.alg_bytes / 1e6),
-                   "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3), "chunks": da.chunk_info()},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
-                     "alg_bytes_per_step": da.alg_bytes, "kernel": "whole matvec step (memset + regular + hanging kernels)"},
-        "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                "ms_per_step": e2e_s * 1e3, "max_rel_diff_vs_device_path": check},
-        "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
-        "ms_per_step_min_max": [min(per_step), max(per_step)],
-    }
-    if args.cpu_baseline:
-        try:
-            cv, cs, sample, _, _ = cpu_reference_run(5, 2)
-            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
-        except Exception as e:  # the bench line must survive a missing oracle
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
-    print(json.dumps(line))
+    alg_total = sum_over_ranks(float(da.alg_bytes))
+    achieved = alg_total / world / (ms * 1e-3) / 1e9   # per-GPU average
+    n_mv_total = sum_over_ranks(float(da.n_mv_elem))
+    n_hang_total = sum_over_ranks(float(da.n_hanging))
+    n_ghost_total = sum_over_ranks(float(da.n_ghost_nodes))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "4D p=1 Laplacian matvec (K_e = h^2 K_ref), space-time moving-ball adaptive tree, class B, "
+                                   "max_level %d of max_depth %d, time window %.4f (grows with the GPU count: ~%.1e elements per GPU)"
+                                   % (level, MAX_DEPTH, width, args.per_gpu_elems),
+                       "dim": DIM, "order": ORDER, "n_elem": n_elem_global, "n_nodes": n_global, "n_visited_elem": int(n_mv_total),
+                       "n_hanging_elem": int(n_hang_total), "n_ghost_nodes": int(n_ghost_total), "tree_class": da.tree_class,
+                       "partition": "SFC-contiguous element ranges, one per GPU; NCCL send/recv ghost exchange" if world > 1 else "single GPU",
+                       "cache": "working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (alg_total / world / 1e6),
+                       "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3), "chunks_rank0": da.chunk_info()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
+                         "alg_bytes_per_step_per_gpu": alg_total / world,
+                         "kernel": "whole matvec step per GPU (memset + chunked regular + hanging kernels" +
+                                   (" + ghost pack/NCCL/unpack)" if world > 1 else ")")},
+            "e2e": {"value": n_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global,
+                    "ms_per_step": e2e_s * 1e3, "max_rel_diff_vs_device_path": check},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "ms_per_step_min_max_rank0": [min(per_step), max(per_step)],
+        }
+        if args.cpu_baseline and world == 1:
+            try:
+                cv, cs, sample, _, _ = cpu_reference_run(5, 2)
+                line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
+            except Exception as e:  # the bench line must survive a missing oracle
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
+        print(json.dumps(line))
     da.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -214,7 +263,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="dkt", choices=["dkt", "reference"])
-    ap.add_argument("--level", type=int, default=7, help="finest level of the moving-ball tree")
+    ap.add_argument("--level", type=int, default=9, help="finest level of the moving-ball tree")
+    ap.add_argument("--per-gpu-elems", type=float, default=1.2e7, help="weak scaling: target elements per GPU (level 9)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

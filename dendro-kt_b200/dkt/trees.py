@@ -91,16 +91,16 @@ def _ball_g(xp, dim, radius, c0, vel, t0, t1):
     return g
 
 
-def moving_ball_tree(dim, max_level, max_depth, min_level=4, radius=0.125, use_torch=False, device="cuda"):
+def moving_ball_tree(dim, max_level, max_depth, min_level=4, radius=0.125, use_torch=False, device="cuda", t0=0.25, t1=0.75):
     """The class-B space-time moving-ball tree (after test/testMovingBall.cpp:
     122-175): a sphere of radius 0.125 centred at (0.375, 0.375+0.25 t, 0.375) for t in
-    [0.25, 0.75], refined to `max_level` at its surface, uniform level-`min_level` (>= 4) guard at the domain
+    [t0, t1] (default [0.25, 0.75]; keep it inside (0.2, 0.8)), refined to `max_level` at its surface, uniform level-`min_level` (>= 4) guard at the domain
     boundary so that no level jump touches it.  For dim < 4 a static ball at (0.375,...)."""
     c0 = (0.375, 0.375, 0.375)
     if use_torch:
         import torch
-        return _refine(torch, dim, max_depth, min_level, max_level, _ball_g(torch, dim, radius, c0, 0.25, 0.25, 0.75), device=device)
-    return _refine(np, dim, max_depth, min_level, max_level, _ball_g(np, dim, radius, c0, 0.25, 0.25, 0.75))
+        return _refine(torch, dim, max_depth, min_level, max_level, _ball_g(torch, dim, radius, c0, 0.25, t0, t1), device=device)
+    return _refine(np, dim, max_depth, min_level, max_level, _ball_g(np, dim, radius, c0, 0.25, t0, t1))
 
 
 def gaussian_points(dim, n, max_depth, seed=7, sigma=0.04, guard_level=None):
