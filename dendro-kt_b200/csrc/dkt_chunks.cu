@@ -398,6 +398,7 @@ struct Mv3Params
   const uint8_t *child;  // hanging set only
   uint32_t nSet, nChunks, elemsPerChunk, xcap, ncap, jdStride;
   int q1mask;
+  int exact_ip;          // order 1: ip0/ip1 equal the exact interpolation to 1e-13
   double lscale[32];
   double ip[2][M * M];
   double ipx[2][M * M];  // ip[0] and J ip[1] J (XOR-permuted coordinates)
@@ -479,6 +480,40 @@ __device__ __forceinline__ void wht(double *v)
   }
 }
 
+// Exact order-1 parent->child interpolation in XOR-permuted coordinates: every axis uses
+// A0 = [[1, 1/2], [0, 1/2]] (input k -> output j), i.e. child'[s] = 2^-|s| * sum_{t subset of s} parent'[t]
+// (a subset-sum transform), and its transpose parent'[t] += sum_{s superset of t} 2^-|s| child'[s].
+template <int N>
+__device__ __forceinline__ void interp_exact(double *v)
+{
+#pragma unroll
+  for (int b = 1; b < N; b <<= 1)
+  {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      if (i & b) continue;
+      v[i | b] = 0.5 * (v[i] + v[i | b]);
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void interp_exact_T(double *v)
+{
+#pragma unroll
+  for (int b = 1; b < N; b <<= 1)
+  {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      if (i & b) continue;
+      const double h = 0.5 * v[i | b];
+      v[i] += h;
+      v[i | b] = h;
+    }
+  }
+}
+
 // eout = K_e ein  (ein is clobbered in the Hadamard form)
 template <int DIM, int ORDER, int OPKIND>
 __device__ __forceinline__ void apply_op3(const Mv3Params<DIM, ORDER> &p, int lev, double *ein, double *eout)
@@ -543,7 +578,7 @@ __device__ __forceinline__ void xor_unpermute(T *v, int c)
 // Walsh-Hadamard operators commute with that permutation (H D H is a convolution on Z_2^dim) and
 // the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
 // work in permuted coordinates throughout; the dense path un-permutes the slot words first.
-template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT>
+template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
 __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? 4 : 3) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
@@ -679,7 +714,8 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
           double ein[N], eout[N], par[N];
 #pragma unroll
           for (int r = 0; r < N; r++) par[r] = (w[N + r] == INVALID) ? 0.0 : un[w[N + r] & 0xFFFFu];
-          tensor_interp3<DIM, M, false>(PERM ? p.ipx : p.ip, child, par);
+          if (EXIP && PERM) interp_exact<N>(par);
+          else tensor_interp3<DIM, M, false>(PERM ? p.ipx : p.ip, child, par);
 #pragma unroll
           for (int r = 0; r < N; r++) ein[r] = (w[r] == INVALID) ? par[r] : un[w[r] & 0xFFFFu];
           apply_op3<DIM, ORDER, OPKIND>(p, lev, ein, eout);
@@ -692,7 +728,8 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
               eout[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
             }
           }
-          tensor_interp3<DIM, M, true>(PERM ? p.ipx : p.ip, child, eout);
+          if (EXIP && PERM) interp_exact_T<N>(eout);
+          else tensor_interp3<DIM, M, true>(PERM ? p.ipx : p.ip, child, eout);
 #pragma unroll
           for (int q = 0; q < N; q++)
           {
@@ -737,7 +774,7 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
   }
 }
 
-template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT>
+template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
 static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, const uint8_t *lev, const uint8_t *child)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
@@ -747,7 +784,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
   const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.jdStride * sizeof(int);
-  auto kern = k_mv3<DIM, ORDER, OPKIND, DIRI, HANG, TPB, NPT>;
+  auto kern = k_mv3<DIM, ORDER, OPKIND, DIRI, HANG, TPB, NPT, EXIP>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TPB, smem));
@@ -767,14 +804,20 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p)
   int rc = DKT_OK;
   if (da.reg.nChunks)
   {
-    if (da.reg.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
+    if (da.reg.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
     if (rc) return rc;
   }
   if (da.hang.nChunks)
   {
-    if (da.hang.maxNloc <= 8u * TPB_H) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+    constexpr bool CAN_EXIP = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
+    const bool exip = CAN_EXIP && p.exact_ip;
+    if (da.hang.maxNloc <= 8u * TPB_H)
+    {
+      if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+    }
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
     if (rc) return rc;
   }
   CK(cudaGetLastError());
@@ -798,6 +841,14 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
       p.ipx[0][k * P::M + j] = da.ip[0][k * P::M + j];
       p.ipx[1][k * P::M + j] = da.ip[1][(P::M - 1 - k) * P::M + (P::M - 1 - j)];
     }
+  p.exact_ip = 0;
+  if (ORDER == 1 && !(flags & DKT_MV_NO_FASTPATH))
+  {
+    const double e0[4] = {1.0, 0.5, 0.0, 0.5}, e1[4] = {0.5, 0.0, 0.5, 1.0};
+    double dev = 0.0;
+    for (int i = 0; i < 4; i++) dev = std::max(dev, std::max(std::fabs(da.ip[0][i] - e0[i]), std::fabs(da.ip[1][i] - e1[i])));
+    p.exact_ip = dev <= 1e-13;
+  }
   bool hadamard = false;
   if (op->kind == DKT_OP_DENSE)
   {
