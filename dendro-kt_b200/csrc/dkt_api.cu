@@ -88,6 +88,17 @@ extern "C"
   {
     return dkt_da_create_dist(dim, order, max_depth, sfc_mode, elem_xyz, elem_lev, n_elem, ip0, ip1, flags, 0, 1, nullptr, out);
   }
+  int dkt_da_export_exchange(const dkt_da *da, uint64_t *send_counts, uint64_t *recv_counts)
+  {
+    if (!da || !send_counts || !recv_counts) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    if (!da->dist.active) { set_error("not a partitioned DA"); return DKT_ERR_INVALID; }
+    for (int p = 0; p < da->dist.nranks; p++)
+    {
+      send_counts[p] = da->dist.send_off[p + 1] - da->dist.send_off[p];
+      recv_counts[p] = da->dist.recv_off[p + 1] - da->dist.recv_off[p];
+    }
+    return DKT_OK;
+  }
   int dkt_da_export_owned_ids(const dkt_da *da, uint32_t *ids)
   {
     if (!da || !ids) { set_error("NULL argument"); return DKT_ERR_INVALID; }
@@ -100,7 +111,7 @@ extern "C"
                          uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, int rank, int nranks,
                          const void *nccl_id, dkt_da **out)
   {
-    if (nranks > 1 && !nccl_id) { set_error("nccl_id is NULL"); return DKT_ERR_INVALID; }
+    if (nranks > 1 && !nccl_id && !(flags & DKT_DIST_DRYRUN)) { set_error("nccl_id is NULL"); return DKT_ERR_INVALID; }
     if (!out) { set_error("out is NULL"); return DKT_ERR_INVALID; }
     *out = nullptr;
     if (dim < 2 || dim > 4) { set_error("dim must be 2, 3 or 4"); return DKT_ERR_INVALID; }
@@ -131,7 +142,7 @@ extern "C"
     else
       exact_interp(order, d.ip);
     int rc = build_da(d, elem_xyz, elem_lev, n_elem, flags);
-    if (rc == DKT_OK && nranks > 1) rc = partition_da(d, h->dist, rank, nranks, nccl_id);
+    if (rc == DKT_OK && nranks > 1) rc = partition_da(d, h->dist, rank, nranks, (flags & DKT_DIST_DRYRUN) ? nullptr : nccl_id);
     if (rc == DKT_OK) rc = build_chunks(d);
     if (rc != DKT_OK)
     {
@@ -231,9 +242,15 @@ extern "C"
     if (!da || !op || !in || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
     DA &d = da->d;
     CKA(cudaSetDevice(d.device));
+    if (da->dist.active && da->dist.nranks > 1 && !da->dist.comm) { set_error("dry-run partition: no communicator"); return DKT_ERR_INVALID; }
     const size_t bytes = (da->dist.active ? da->dist.nOwned : d.nNodes) * sizeof(double);
     const double *din = in;
     double *dout = out;
+    if ((flags & DKT_VEC_GHOSTED) && (!(flags & DKT_VEC_DEVICE) || !da->dist.active))
+    {
+      set_error("DKT_VEC_GHOSTED needs device vectors on a partitioned DA");
+      return DKT_ERR_INVALID;
+    }
     if (!(flags & DKT_VEC_DEVICE))
     {
       if (!d.d_in)

@@ -63,9 +63,12 @@ constexpr uint32_t META_SHARED = 0x8000u;
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
+#ifndef DKT_ROWS
+#define DKT_ROWS 256
+#endif
 int rows_per_chunk(int N)
 {
-  int r = std::min(SLOT_CAP / N, 256);
+  int r = std::min(SLOT_CAP / N, DKT_ROWS);
   return r & ~1;
 }
 
@@ -579,7 +582,7 @@ __device__ __forceinline__ void xor_unpermute(T *v, int c)
 // the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
 // work in permuted coordinates throughout; the dense path un-permutes the slot words first.
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
-__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? 4 : 3) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
+__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? 4 : 3) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int M = ORDER + 1;
@@ -799,8 +802,8 @@ template <int DIM, int ORDER, int OPKIND, bool DIRI>
 static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
-  constexpr int TPB_R = (N == 27) ? 160 : 256;  // >= elements per chunk (one element per thread)
-  constexpr int TPB_H = (N == 27) ? 96 : 128;
+  constexpr int TPB_R = (N == 27) ? 160 : DKT_ROWS;  // >= elements per chunk (one element per thread)
+  constexpr int TPB_H = (N == 27) ? 96 : DKT_ROWS / 2;
   int rc = DKT_OK;
   if (da.reg.nChunks)
   {

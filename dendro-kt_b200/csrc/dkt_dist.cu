@@ -179,6 +179,24 @@ __global__ void k_lower_bound(const uint32_t *a, uint64_t n, uint32_t key, uint6
   }
   *out = lo;
 }
+// weight of the element at each tree position (visited list = [regular | hanging], d_mv_src = position)
+__global__ void k_weights(const uint32_t *src, uint64_t nMv, uint64_t nReg, uint64_t wr, uint64_t wh, uint64_t *w)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < nMv) w[src[i]] = i < nReg ? wr : wh;
+}
+__global__ void k_lower_bound64(const uint64_t *a, uint64_t n, uint64_t key, uint64_t *out)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  *out = lo;
+}
 __global__ void k_pack(const double *v, const uint32_t *idx, uint64_t n, double *buf)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -235,9 +253,36 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   const uint64_t nMv = g.nMv, nReg = g.nReg, nHang = g.nHang, nNodes = g.nNodes;
   dist.nGlobalNodes = nNodes;
   dist.nGlobalElems = g.nElem;
+  // ---- SFC-contiguous ranges of equal WEIGHT: a hanging element (two slot rows, interpolation both
+  //      ways) costs about as much as HANG_WEIGHT/REG_WEIGHT regular ones in the chunked kernels
   Bounds B;
   B.nranks = nranks;
-  for (int p = 0; p <= nranks; p++) B.b[p] = (uint32_t)((nMv * (uint64_t)p) / (uint64_t)nranks);
+  {
+    constexpr uint64_t REG_WEIGHT = 4, HANG_WEIGHT = 9;
+    uint64_t *wsrc = nullptr, *wscan = nullptr, *dbound = nullptr;
+    CK(cudaMalloc((void **)&wsrc, (nMv + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&wscan, (nMv + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&dbound, (nranks + 1) * sizeof(uint64_t)));
+    CK(cudaMemsetAsync(wsrc, 0, (nMv + 1) * sizeof(uint64_t), g.stream));
+    LAUNCHS(k_weights, nMv, g.stream, g.d_mv_src, nMv, nReg, REG_WEIGHT, HANG_WEIGHT, wsrc);
+    rc = device_exclusive_scan(g, wsrc, wscan, nMv + 1);
+    if (rc) return rc;
+    uint64_t W = 0;
+    CK(cudaMemcpy(&W, wscan + nMv, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (int p = 0; p <= nranks; p++)
+    {
+      k_lower_bound64<<<1, 1, 0, g.stream>>>(wscan, nMv + 1, (W * (uint64_t)p) / (uint64_t)nranks, dbound + p);
+      g_launches++;
+    }
+    std::vector<uint64_t> hb(nranks + 1);
+    // g.stream is a non-blocking stream: a plain cudaMemcpy would not wait for the kernels above
+    CK(cudaMemcpyAsync(hb.data(), dbound, (nranks + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int p = 0; p <= nranks; p++) B.b[p] = (uint32_t)std::min<uint64_t>(hb[p], nMv);
+    B.b[0] = 0;
+    B.b[nranks] = (uint32_t)nMv;
+    cudaFree(wsrc); cudaFree(wscan); cudaFree(dbound);
+  }
 
   // ---- ownership and reference masks ------------------------------------------------------------------
   uint32_t *minsrc = nullptr;
@@ -364,7 +409,7 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   cudaFree(minsrc); cudaFree(refmask); cudaFree(flag); cudaFree(wide); cudaFree(pos); cudaFree(g2l); cudaFree(l2g);
 
   // ---- communicator ------------------------------------------------------------------------------------------------------
-  if (nranks > 1)
+  if (nranks > 1 && nccl_id)
   {
     ncclUniqueId_t id;
     std::memcpy(&id, nccl_id, sizeof(id));
@@ -382,7 +427,12 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
   cudaStream_t s = da.stream;
   const uint64_t nOwned = d.nOwned;
   const uint64_t totalSend = d.send_off[d.nranks];
-  CK(cudaMemcpyAsync(d.d_in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  // DKT_VEC_GHOSTED: the caller's vectors already have room for the ghost segment ([owned | ghosts],
+  // like the reference's ghosted vectors) and are used in place - no staging copies
+  const bool ghosted = (flags & DKT_VEC_GHOSTED) != 0;
+  double *in_local = ghosted ? const_cast<double *>(d_in) : d.d_in_local;
+  double *out_local = ghosted ? d_out : d.d_out_local;
+  if (!ghosted) CK(cudaMemcpyAsync(in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (d.nranks > 1)
   {
     // readFromGhost: owners -> ghosts, received straight into the ghost segments of the local vector
@@ -393,13 +443,13 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
       if (p == d.rank) continue;
       const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
       if (sc) NCK(g_nccl.Send(d.d_send_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
-      if (rcv) NCK(g_nccl.Recv(d.d_in_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (rcv) NCK(g_nccl.Recv(in_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
     }
     NCK(g_nccl.GroupEnd());
     g_launches++;
   }
-  int rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, d.d_in_local, d.d_out_local, scale, flags)
-                                 : run_matvec_chunked(da, op, d.d_in_local, d.d_out_local, scale, flags);
+  int rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
+                                 : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
   if (rc) return rc;
   if (d.nranks > 1)
   {
@@ -409,14 +459,14 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
     {
       if (p == d.rank) continue;
       const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
-      if (rcv) NCK(g_nccl.Send(d.d_out_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (rcv) NCK(g_nccl.Send(out_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
       if (sc) NCK(g_nccl.Recv(d.d_recv_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
     }
     NCK(g_nccl.GroupEnd());
     g_launches++;
-    LAUNCHS(k_unpack_add, totalSend, s, d.d_out_local, d.d_send_idx, totalSend, d.d_recv_buf);
+    LAUNCHS(k_unpack_add, totalSend, s, out_local, d.d_send_idx, totalSend, d.d_recv_buf);
   }
-  CK(cudaMemcpyAsync(d_out, d.d_out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return DKT_OK;
 }
 } // namespace dkt

@@ -35,12 +35,16 @@ extern "C" {
 #define DKT_ELEMS_ON_DEVICE 1u  /* elem_xyz / elem_lev are device pointers                  */
 #define DKT_ELEMS_PRESORTED 2u  /* elements already in tree order (skip the SFC sort)        */
 #define DKT_ALLOW_UNDEFINED 4u  /* build class-U trees anyway (intended semantics, unpinned) */
+#define DKT_DIST_DRYRUN 8u      /* dkt_da_create_dist: build rank's tables but no communicator (nccl_id may be
+                                   NULL); for inspecting the partition on one GPU - dkt_matvec then fails */
 
 /* dkt_matvec flags */
 #define DKT_VEC_HOST 0u    /* in/out are host pointers: H2D, matvec, D2H                    */
 #define DKT_VEC_DEVICE 1u  /* in/out are device pointers on the DA's device                */
 #define DKT_NO_Q1_MASK 2u  /* mathematically consistent transpose (NOT the reference's)    */
 #define DKT_MV_FLAT 4u     /* use the flat gather/atomic kernels instead of the chunked ones */
+#define DKT_VEC_GHOSTED 16u /* partitioned DA, device vectors: in/out hold n_nodes + n_ghost_nodes entries
+                              ([owned | ghosts], like the reference's ghosted vectors) and are used in place */
 #define DKT_MV_NO_FASTPATH 8u /* apply kref as a dense matrix even if it has Walsh-Hadamard diagonal form */
 
 /* tree classes */
@@ -120,6 +124,8 @@ int dkt_da_create_dist(int dim, int order, int max_depth, int sfc_mode, const ui
                        uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, int rank, int nranks,
                        const void *nccl_id, dkt_da **out);
 int dkt_da_export_owned_ids(const dkt_da *da, uint32_t *ids);
+/* send_counts[p] = owned nodes rank p ghosts, recv_counts[p] = this rank's ghosts owned by p (n_ranks each) */
+int dkt_da_export_exchange(const dkt_da *da, uint64_t *send_counts, uint64_t *recv_counts);
 
 int dkt_da_sizes(const dkt_da *da, dkt_sizes *out);
 /* tree in DA order: what DA::getTreePartFront()/Back() bracket (include/oda.h:255-258) */

@@ -28,6 +28,13 @@ def gathered_matvec(da, op, u_global, n_global, rank, world, **kw):
     u_loc = torch.from_numpy(u_global).cuda()[ids].contiguous()
     v_loc = da.matvec(op, u_loc, **kw)
     torch.cuda.synchronize()
+    # the in-place ghosted-vector path must give the same owned values
+    ug = torch.zeros(da.n_nodes + da.n_ghost_nodes, dtype=torch.float64, device="cuda")
+    ug[:da.n_nodes] = u_loc
+    vg = torch.empty_like(ug)
+    da.matvec(op, ug, vg, ghosted=True, **kw)
+    torch.cuda.synchronize()
+    assert float((vg[:da.n_nodes] - v_loc).abs().max()) <= 1e-12 * max(float(v_loc.abs().max()), 1e-300)
     full = torch.zeros(n_global, dtype=torch.float64, device="cuda")
     full[ids] = v_loc
     owned = torch.zeros(n_global, dtype=torch.float64, device="cuda")

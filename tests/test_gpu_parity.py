@@ -161,6 +161,37 @@ def test_properties_at_scale(dkt):
         da.close()
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_partition_tables_are_consistent(dkt, nranks):
+    """All ranks' partitions built on ONE GPU (dry run, no communicator): every node has exactly one
+    owner, what r sends to p is what p expects from r, element work is split by weight."""
+    dim, md = 4, 10
+    xyz, lev = dkt.trees.moving_ball_tree(dim, 5, md)
+    da1 = dkt.DA(xyz, lev, dim, 1, md)
+    n_global, n_mv = da1.n_nodes, da1.n_mv_elem
+    da1.close()
+    owned_all, send, recv, work = [], [], [], []
+    for r in range(nranks):
+        da = dkt.DA(xyz, lev, dim, 1, md, rank=r, nranks=nranks, dryrun=True)
+        assert da.n_global_nodes == n_global
+        owned_all.append(da.owned_ids())
+        sc, rc = da.exchange_counts()
+        send.append(sc)
+        recv.append(rc)
+        work.append(4 * (da.n_mv_elem - da.n_hanging) + 9 * da.n_hanging)
+        assert da.n_nodes > 0 and da.n_mv_elem > 0
+        with pytest.raises(dkt.DktError):
+            da.matvec(dkt.Operator.identity(), np.zeros(da.n_nodes))
+        da.close()
+    allo = np.concatenate(owned_all)
+    assert len(allo) == n_global and len(np.unique(allo)) == n_global
+    for r in range(nranks):
+        for p in range(nranks):
+            assert send[r][p] == recv[p][r]
+        assert send[r][r] == 0 and recv[r][r] == 0
+    assert max(work) <= 1.05 * (sum(work) / nranks) + 9 * 256
+
+
 def test_class_u_tree_is_refused(dkt):
     """The stock testMovingBall sphere (test/testMovingBall.cpp:122-175) touches the domain
     boundary with level jumps -> the reference reads undefined values; the library refuses."""
