@@ -1,6 +1,7 @@
 // C ABI of libdkt.so (declared in include/dkt.h).
 #include "dkt_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -274,6 +275,36 @@ extern "C"
       CKA(cudaStreamSynchronize(d.stream));
     }
     return DKT_OK;
+  }
+
+  int dkt_cg_solve(dkt_da *da, const dkt_op *op, double *x, const double *b, int max_iter, double *tol, double scale,
+                   unsigned flags, int *iters, int *status)
+  {
+    if (!da || !op || !x || !b || !tol || !iters || !status) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    if (flags & DKT_VEC_GHOSTED) { set_error("dkt_cg_solve takes owned-length vectors"); return DKT_ERR_INVALID; }
+    DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    if (da->dist.active && da->dist.nranks > 1 && !da->dist.comm) { set_error("dry-run partition: no communicator"); return DKT_ERR_INVALID; }
+    const size_t bytes = (da->dist.active ? da->dist.nOwned : d.nNodes) * sizeof(double);
+    double *dx = x;
+    const double *db = b;
+    double *tmp = nullptr;
+    if (!(flags & DKT_VEC_DEVICE))
+    {
+      CKA(cudaMalloc((void **)&tmp, 2 * std::max<size_t>(bytes, 8)));
+      dx = tmp;
+      db = tmp + bytes / sizeof(double);
+      CKA(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, d.stream));
+      CKA(cudaMemcpyAsync((void *)db, b, bytes, cudaMemcpyHostToDevice, d.stream));
+    }
+    const int rc = cg_solve(d, &da->dist, op, dx, db, max_iter, tol, scale, flags, iters, status);
+    if (rc == DKT_OK && !(flags & DKT_VEC_DEVICE))
+    {
+      CKA(cudaMemcpyAsync(x, dx, bytes, cudaMemcpyDeviceToHost, d.stream));
+      CKA(cudaStreamSynchronize(d.stream));
+    }
+    cudaFree(tmp);
+    return rc;
   }
 
   int dkt_last_kernel_ms(dkt_da *da, float *ms)

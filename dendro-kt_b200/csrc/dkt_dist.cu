@@ -51,6 +51,7 @@ struct NcclApi
   int (*CommDestroy)(ncclComm_p) = nullptr;
   int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -74,7 +75,7 @@ static int load_nccl()
   if (!g_nccl.field) { set_error(std::string("libnccl lacks ") + name); return DKT_ERR_NCCL; }
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
   SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-  SYM(GetErrorString, "ncclGetErrorString")
+  SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce")
 #undef SYM
   return DKT_OK;
 }
@@ -229,6 +230,14 @@ static int positions(DA &g, const uint8_t *flag, uint64_t n, uint64_t *wide, uin
   int rc = device_exclusive_scan(g, wide, pos, n + 1);
   if (rc) return rc;
   CK(cudaMemcpy(&total, pos + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DKT_OK;
+}
+
+int dist_allreduce(Dist &d, double *red, cudaStream_t s)
+{
+  if (!d.comm) { set_error("no communicator"); return DKT_ERR_NCCL; }
+  NCK(g_nccl.AllReduce(red, red, 2, NCCL_FLOAT64, 0 /* ncclSum */, (ncclComm_p)d.comm, s));
+  NCK(g_nccl.AllReduce(red + 2, red + 2, 1, NCCL_FLOAT64, 2 /* ncclMax */, (ncclComm_p)d.comm, s));
   return DKT_OK;
 }
 

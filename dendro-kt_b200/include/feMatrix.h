@@ -27,6 +27,7 @@ protected:
   std::vector<double> m_kref;
   double m_alpha = 0.0, m_opScale = 0.0;
   bool m_opReady = false;
+  int m_lastIters = 0;
   std::vector<VECType> m_inGhosted, m_outGhosted;  // members, not function statics: re-entrant per object
 
 public:
@@ -64,6 +65,26 @@ public:
     da->template ghostedNodalToNodalVec<VECType>(outG, out, true, m_uiDof);
     asLeaf().postMatVec(outG + da->getLocalNodeBegin(), out, scale);
   }
+
+  /** HeatMat::cgSolve (FEM/examples/src/heatMat.cpp:165-325) with every vector resident on the GPU: x is
+   *  the initial guess on entry and the solution on return, tol returns the achieved |r|_inf/|b|_inf.
+   *  `dirichletRows` stands for the leaf's pre/postMatVec boundary zeroing (host hooks cannot run inside
+   *  the resident loop).  Returns 0 if converged within max_iter, 1 otherwise. */
+  int cgSolve(double *x, double *b, int max_iter, double &tol, bool dirichletRows = true, double scale = 1.0)
+  {
+    ot::DA<dim> *da = feMat<dim>::m_uiOctDA;
+    ensureDeviceOperator(scale);
+    dkt_op op;
+    op.kind = DKT_OP_DENSE;
+    op.kref = m_kref.data();
+    op.alpha = m_alpha;
+    op.dirichlet = dirichletRows ? 1 : 0;
+    int iters = 0, status = 1;
+    dkt_host::check(dkt_cg_solve(da->handle(), &op, x, b, max_iter, &tol, 1.0, DKT_VEC_HOST, &iters, &status), "feMatrix::cgSolve");
+    m_lastIters = iters;
+    return status;
+  }
+  int lastIterations() const { return m_lastIters; }
 
   /** the recovered reference-cell matrix and level exponent (after the first matVec) */
   const std::vector<double> &deviceKref() const { return m_kref; }

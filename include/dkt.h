@@ -148,6 +148,15 @@ int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, ui
  * rank.  in/out have n_nodes doubles in DA order. */
 int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags);
 
+/* Conjugate gradients with every vector resident in HBM: the solver of the reference's example
+ * operator, HeatMat::cgSolve(x, b, max_iter, tol) (FEM/examples/src/heatMat.cpp:165-325) - same
+ * recurrences, same stopping rule |r|_inf / |b|_inf <= tol.  x (initial guess in, solution out) and b
+ * are host or device vectors as selected by `flags` (DKT_VEC_*); *tol returns the achieved residual,
+ * *iters the iterations done, *status 0 if converged within max_iter, 1 otherwise (the reference's
+ * return value).  Each iteration is one dkt_matvec plus two fused vector kernels. */
+int dkt_cg_solve(dkt_da *da, const dkt_op *op, double *x, const double *b, int max_iter, double *tol, double scale,
+                 unsigned flags, int *iters, int *status);
+
 /* Device time of the kernels of the most recent dkt_matvec on this DA, in milliseconds
  * (CUDA events on the DA's stream; excludes H2D/D2H). */
 int dkt_last_kernel_ms(dkt_da *da, float *ms);

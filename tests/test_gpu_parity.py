@@ -192,18 +192,85 @@ def test_partition_tables_are_consistent(dkt, nranks):
     assert max(work) <= 1.05 * (sum(work) / nranks) + 9 * 256
 
 
-def test_class_u_tree_is_refused(dkt):
-    """The stock testMovingBall sphere (test/testMovingBall.cpp:122-175) touches the domain
-    boundary with level jumps -> the reference reads undefined values; the library refuses."""
+def _oracle_cg(t, K, alpha, b, max_iter, tol):
+    """HeatMat::cgSolve (FEM/examples/src/heatMat.cpp:165-325) on top of the oracle matvec."""
+    mv = lambda x: flat.matvec(t, x, K, alpha=alpha, dirichlet=True)
+    x = np.zeros_like(b)
+    normb = np.abs(b).max() or 1.0
+    r0 = b - mv(x)
+    p = r0.copy()
+    resid = np.abs(r0).max() / normb
+    it = 0
+    for it in range(1, max_iter + 1):
+        Ap = mv(p)
+        a = (r0 @ r0) / (p @ Ap)
+        x += a * p
+        r1 = r0 - a * Ap
+        resid = np.abs(r1).max() / normb
+        if resid <= tol:
+            break
+        beta = (r1 @ r1) / (r0 @ r0)
+        p = r1 + beta * p
+        r0 = r1
+    return x, it, resid
+
+
+def test_resident_cg_solver(dkt):
+    """dkt_cg_solve = HeatMat::cgSolve with resident vectors: (a) converges on a uniform grid (SPD
+    operator) to the manufactured solution; (b) on an adaptive tree follows the oracle's iterates."""
+    import torch
     dim, md = 3, 10
-    xyz, lev = dkt.trees.moving_ball_tree(dim, 6, md, min_level=2, radius=0.36)
-    t = flat.build_tables(xyz, lev, dim, 1, md)
-    if t.tree_class != "U":
-        pytest.skip("generator did not produce a class-U tree")
+    xyz, lev = dkt.trees.uniform_tree(dim, 4, md)
+    da = dkt.DA(xyz, lev, dim, 1, md)
+    K = dkt.operators.laplace_kref(dim, 1)
+    op = dkt.Operator.dense(K, dim - 2.0, dirichlet=True)
+    xt = cases.input_vector(da.n_nodes)
+    xt[da.boundary_ids()] = 0.0
+    b = da.matvec(op, xt)
+    x, it, resid, ok = da.cg_solve(op, b, max_iter=500, tol=1e-11)
+    assert ok and resid <= 1e-11 and it < 500
+    assert np.abs(x - xt).max() <= 1e-8 * np.abs(xt).max()
+    xd, it2, _, ok2 = da.cg_solve(op, torch.from_numpy(b).cuda(), max_iter=500, tol=1e-11)  # device vectors
+    assert ok2 and it2 == it and np.abs(xd.cpu().numpy() - x).max() <= 1e-12 * np.abs(x).max()
+    da.close()
+    case = load_case("ball-d3-p1-morton-6")
+    t = cases.oracle_tables_for(case)
+    da = dkt.DA(case["xyz"], case["lev"], 3, 1, case["max_depth"])
+    bb = cases.input_vector(da.n_nodes, seed=4)
+    bb[da.boundary_ids()] = 0.0
+    xo, ito, ro = _oracle_cg(t, K, 1.0, bb, 12, 0.0)
+    xg, itg, rg, _ = da.cg_solve(op, bb, max_iter=12, tol=0.0)
+    assert itg == ito == 12
+    assert np.abs(xg - xo).max() <= 1e-9 * np.abs(xo).max() and abs(rg - ro) <= 1e-9 * ro
+    da.close()
+
+
+def class_u_tree():
+    """A ball of radius 0.25 centred at 0.25 (the stock testMovingBall parameters,
+    test/testMovingBall.cpp:122-175) touches the domain boundary with level jumps."""
+    import dkt as m
+    g = m.trees._ball_g(np, 4, 0.25, (0.25, 0.25, 0.25), 0.25, 0.25, 0.75)
+    return m.trees._refine(np, 4, 10, 2, 4, g)
+
+
+def test_class_u_tree_is_refused(dkt):
+    """On such a tree the reference reads undefined parent values (FEM/include/matvec.h:439-447);
+    the library detects it at construction and refuses unless told otherwise."""
+    xyz, lev = class_u_tree()
+    t = flat.build_tables(xyz, lev, 4, 1, 10)
+    assert t.tree_class == "U"
     with pytest.raises(dkt.DktError, match="class-U"):
-        dkt.DA(xyz, lev, dim, 1, md)
-    da = dkt.DA(xyz, lev, dim, 1, md, allow_undefined=True)
-    assert da.tree_class == "U"
+        dkt.DA(xyz, lev, 4, 1, 10)
+    da = dkt.DA(xyz, lev, 4, 1, 10, allow_undefined=True)
+    assert da.tree_class == "U" and da.n_mv_elem == len(t.mv_lev)
+    nx, nl = da.nodes()
+    assert np.array_equal(nx, t.node_xyz) and np.array_equal(nl, t.node_lev)
+    # with absent parents read as zero (the intended semantics) both sides still agree
+    u = cases.input_vector(da.n_nodes)
+    K = dkt.operators.laplace_kref(4, 1)
+    v = da.matvec(dkt.Operator.dense(K, 2.0), u)
+    vo = flat.matvec(t, u, K, alpha=2.0)
+    assert np.abs(v - vo).max() <= TOL * np.abs(vo).max()
     da.close()
 
 
