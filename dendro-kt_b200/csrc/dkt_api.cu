@@ -264,6 +264,8 @@ extern "C"
       dout = d.d_out;
     }
     CKA(cudaEventRecord(d.ev0, d.stream));
+    // the chunk tables carry quirk Q1 statically; the conservative variant runs on the flat kernels
+    if (flags & DKT_NO_Q1_MASK) flags |= DKT_MV_FLAT;
     const int rc = da->dist.active ? run_matvec_dist(d, da->dist, op, din, dout, scale, flags)
                    : (flags & DKT_MV_FLAT) ? run_matvec(d, op, din, dout, scale, flags)
                                            : run_matvec_chunked(d, op, din, dout, scale, flags);

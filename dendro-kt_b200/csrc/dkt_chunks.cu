@@ -58,6 +58,7 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;  // 4096 slots per chunk
 constexpr int MAX_LEN = 511;                         // run length of a node inside a chunk (9 bits)
 constexpr uint32_t META_LEN = 0x1FFu;
+constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty: only read by this chunk)
 constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
 
@@ -75,10 +76,26 @@ int rows_per_chunk(int N)
 // ------------------------------------------------------------------------------------------
 // build
 // ------------------------------------------------------------------------------------------
-__global__ void k_ref_count(const uint32_t *ids, uint64_t n, uint32_t *cnt)
+// Number of WRITING references of every node.  Own-lattice slots always write; a parent-lattice slot q
+// of a hanging element writes only if the element's own rank q is unfilled (quirk Q1 is static in the
+// chunk tables: FEM/include/matvec.h:517) - `own` is the element's e2n row, null for the own rows.
+__global__ void k_ref_count(const uint32_t *ids, const uint32_t *own, uint64_t n, uint32_t *cnt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n && ids[i] != INVALID) atomicAdd(cnt + ids[i], 1u);
+  if (i >= n || ids[i] == INVALID) return;
+  if (own && own[i] != INVALID) return;  // read-only parent slot
+  atomicAdd(cnt + ids[i], 1u);
+}
+// bit s of fmask[h]: own slot s of hanging element h is filled (slot order, i.e. XOR-permuted at order 1)
+__global__ void k_fmask(const uint32_t *e2n_hang, const uint8_t *child_hang, uint64_t nHang, int N, int xorperm, uint32_t *fmask)
+{
+  uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (h >= nHang) return;
+  const int c = xorperm ? child_hang[h] : 0;
+  uint32_t m = 0;
+  for (int q = 0; q < N; q++)
+    if (e2n_hang[h * N + q] != INVALID) m |= 1u << (q ^ c);
+  fmask[h] = m;
 }
 
 // One CTA per chunk.  WRITE == false: only report the chunk's node count and longest run.
@@ -97,10 +114,12 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
     typename SortPairs::TempStorage pairs;
     typename SortKeys::TempStorage keys;
     typename Scan::TempStorage scan;
+    uint16_t newrank[SLOT_CAP];                // by gid-rank: rank after the (len desc) re-sort (after the sorts)
   } tmp;
+  uint16_t *s_newrank = tmp.newrank;
   __shared__ uint32_t s_last[SORT_THREADS];
-  __shared__ uint16_t s_start[SLOT_CAP + 1];   // by gid-rank: first sorted position of the node's run
-  __shared__ uint16_t s_newrank[SLOT_CAP];     // by gid-rank: rank after the (len desc) re-sort
+  __shared__ uint16_t s_start[SLOT_CAP + 1];   // by gid-rank: first sorted position of the node's references
+  __shared__ uint16_t s_cw[SLOT_CAP + 1];      // by gid-rank: number of WRITING references sorted before the node
   __shared__ int s_hist[MAX_LEN + 2];
   __shared__ int s_jd[MAX_LEN + 2];
   __shared__ int s_total, s_P, s_maxlen;
@@ -163,10 +182,42 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
     }
   }
   if (threadIdx.x == 0) s_total = total;
+  // writing references: every valid own-lattice slot; parent-lattice slots only where the element's
+  // own rank is unfilled (static Q1).  k-th WRITING reference of a node -> diagonal k.
+  int wr[SORT_ITEMS];
+  int nwr = 0;
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++)
+  {
+    wr[i] = 0;
+    if (key[i] != INVALID)
+    {
+      const int q = val[i] % spe, el = val[i] / spe;
+      wr[i] = (q < N) ? 1 : (e2n[(elem0 + e0 + el) * N + (q - N)] == INVALID);
+    }
+    nwr += wr[i];
+  }
+  __syncthreads();
+  int wbefore = 0, wtotal = 0;
+  Scan(tmp.scan).ExclusiveSum(nwr, wbefore, wtotal);
+  uint16_t cwi[SORT_ITEMS];
+  {
+    int acc = wbefore;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++)
+    {
+      cwi[i] = (uint16_t)acc;
+      if (head[i]) s_cw[rank0[i]] = (uint16_t)acc;
+      acc += wr[i];
+    }
+  }
   __syncthreads();
   const int nloc = s_total;
-  const int P = s_P;
-  if (threadIdx.x == 0) s_start[nloc] = (uint16_t)P;
+  if (threadIdx.x == 0)
+  {
+    s_start[nloc] = (uint16_t)s_P;
+    s_cw[nloc] = (uint16_t)wtotal;
+  }
   __syncthreads();
   // second sort: nodes by (len descending, gid-rank ascending)
   uint32_t k2[SORT_ITEMS];
@@ -177,7 +228,7 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
     k2[i] = INVALID;
     if (n < nloc)
     {
-      const int len = (int)s_start[n + 1] - (int)s_start[n];
+      const int len = (int)s_cw[n + 1] - (int)s_cw[n];  // writing references only
       k2[i] = ((uint32_t)(MAX_LEN - min(len, MAX_LEN)) << 12) | (uint32_t)n;
       atomicAdd(&s_hist[min(len, MAX_LEN + 1)], 1);
       atomicMax(&s_maxlen, len);
@@ -194,6 +245,7 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
     return;
   }
   SortKeys(tmp.keys).Sort(k2, 0, 21);
+  __syncthreads();  // tmp is re-used as newrank[]
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++)
   {
@@ -245,19 +297,22 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
       q = (q < N) ? (q ^ cnum) : (N + ((q - N) ^ cnum));
     }
     const uint64_t dst = e0 * spe + (uint64_t)q * elemsPerChunk + el;
+    // absent node: read the chunk's zero entry un[nloc], write to the trash position behind the diagonals
+    const uint32_t trash = (uint32_t)s_jd[MAX_LEN + 1];
     if (key[i] == INVALID)
     {
-      if (val[i] < nslots) slot[dst] = INVALID;
+      if (val[i] < nslots) slot[dst] = (uint32_t)nloc | (trash << 16);
       continue;
     }
     const int n0 = rank0[i];
-    const int k = posn - (int)s_start[n0];
+    const int k = (int)cwi[i] - (int)s_cw[n0];
     const int nr = s_newrank[n0];
-    slot[dst] = (uint32_t)nr | ((uint32_t)(s_jd[k] + nr) << 16);
+    slot[dst] = (uint32_t)nr | ((wr[i] ? (uint32_t)(s_jd[k] + nr) : trash) << 16);
+    (void)posn;
     if (head[i])
     {
-      const int len = (int)s_start[n0 + 1] - (int)s_start[n0];
-      uint32_t m = (uint32_t)len;
+      const int len = (int)s_cw[n0 + 1] - (int)s_cw[n0];
+      uint32_t m = (uint32_t)len | META_PRESENT;
       if (refcnt[key[i]] != (uint32_t)len) m |= META_SHARED;
       if (isbdy[key[i]]) m |= META_BDY;
       gid_out[noff + nr] = key[i];
@@ -343,7 +398,9 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
 void free_chunks(DA &da)
 {
   cudaFree(da.d_mv_child);
+  cudaFree(da.d_fmask);
   da.d_mv_child = nullptr;
+  da.d_fmask = nullptr;
   for (ChunkSet *cs : {&da.reg, &da.hang})
   {
     cudaFree(cs->d_slot); cudaFree(cs->d_gid); cudaFree(cs->d_meta); cudaFree(cs->d_jd); cudaFree(cs->d_node_off);
@@ -371,8 +428,15 @@ int build_chunks(DA &da)
   CK(cudaMalloc((void **)&refcnt, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t)));
   CK(cudaMemsetAsync(refcnt, 0, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t), da.stream));
   const uint64_t n1 = da.nMv * (uint64_t)da.N, n2 = da.nHang * (uint64_t)da.N;
-  if (n1) { k_ref_count<<<(unsigned)((n1 + 255) / 256), 256, 0, da.stream>>>(da.d_e2n, n1, refcnt); g_launches++; }
-  if (n2) { k_ref_count<<<(unsigned)((n2 + 255) / 256), 256, 0, da.stream>>>(da.d_pnode, n2, refcnt); g_launches++; }
+  if (n1) { k_ref_count<<<(unsigned)((n1 + 255) / 256), 256, 0, da.stream>>>(da.d_e2n, nullptr, n1, refcnt); g_launches++; }
+  if (n2)
+  {
+    k_ref_count<<<(unsigned)((n2 + 255) / 256), 256, 0, da.stream>>>(da.d_pnode, da.d_e2n + da.nReg * (uint64_t)da.N, n2, refcnt);
+    CK(cudaMalloc((void **)&da.d_fmask, da.nHang * sizeof(uint32_t)));
+    k_fmask<<<(unsigned)((da.nHang + 255) / 256), 256, 0, da.stream>>>(da.d_e2n + da.nReg * (uint64_t)da.N, da.d_mv_child + da.nReg, da.nHang,
+                                                                       da.N, da.order == 1 ? 1 : 0, da.d_fmask);
+    g_launches += 2;
+  }
   int rc = build_set(da, da.reg, 0, da.nReg, 1, refcnt);
   if (rc == DKT_OK) rc = build_set(da, da.hang, da.nReg, da.nHang, 2, refcnt);
   cudaFree(refcnt);
@@ -398,7 +462,8 @@ struct Mv3Params
   const uint16_t *jd;
   const uint64_t *node_off;
   const uint8_t *lev;    // level of the set's elements
-  const uint8_t *child;  // hanging set only
+  const uint8_t *child;  // Morton child numbers of the set's elements
+  const uint32_t *fmask; // hanging set: filled own slots (slot order)
   uint32_t nSet, nChunks, elemsPerChunk, xcap, ncap, jdStride;
   int q1mask;
   int exact_ip;          // order 1: ip0/ip1 equal the exact interpolation to 1e-13
@@ -614,17 +679,19 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
       }
     }
   };
-  auto issue_gather = [&](double *un, const uint32_t *g, const uint16_t *m) {
+  auto issue_gather = [&](double *un, const uint32_t *g, const uint16_t *m, int nloc) {
+    if (tid == 0) un[nloc] = 0.0;  // the entry absent nodes read
 #pragma unroll
     for (int k = 0; k < NPT; k++)
     {
       const int n = tid + k * TPB;
-      if ((m[k] & META_LEN) == 0) continue;  // no such node
+      if (!(m[k] & META_PRESENT)) continue;  // no such node
       if (DIRI && (m[k] & META_BDY)) un[n] = 0.0;
       else cp_async8(un + n, p.in + g[k]);
     }
   };
   uint32_t w[ROWS * N];
+  uint32_t fm = 0;
   int lev = 0, child = 0;
   auto load_slots = [&](uint64_t cc) {
     const uint64_t e0 = cc * (uint64_t)E;
@@ -636,10 +703,18 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
       for (int r = 0; r < ROWS * N; r++) w[r] = sw[(uint32_t)r * E];
       lev = p.lev[e0 + tid];
       if (HANG || (ORDER == 1 && OPKIND == DKT_OP_DENSE)) child = p.child[e0 + tid];
+      if (HANG) fm = p.fmask[e0 + tid];
       if (ORDER == 1 && OPKIND == DKT_OP_DENSE)
       {  // natural rank order for the dense product
         xor_unpermute<DIM, N, uint32_t>(w, child);
-        if (HANG) xor_unpermute<DIM, N, uint32_t>(w + N, child);
+        if (HANG)
+        {
+          xor_unpermute<DIM, N, uint32_t>(w + N, child);
+          uint32_t nat = 0;
+#pragma unroll
+          for (int r = 0; r < N; r++) nat |= ((fm >> (r ^ child)) & 1u) << r;
+          fm = nat;
+        }
       }
     }
   };
@@ -648,7 +723,7 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
   // ---- prologue: everything for the first chunk ------------------------------------------------
   uint64_t offA = p.node_off[c], offB = p.node_off[c + 1];
   load_nodes(offA, offB, gidC, metaC);
-  issue_gather(unb, gidC, metaC);
+  issue_gather(unb, gidC, metaC, (int)(offB - offA));
   cp_async_commit();
   for (int k = tid; k < (int)p.jdStride; k += TPB) jdb[k] = p.jd[c * (uint64_t)p.jdStride + k];
   load_slots(c);
@@ -714,39 +789,37 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
         }
         else
         {
+          // absent nodes read un[nloc] == 0 and write to a trash position, read-only parent slots (static
+          // Q1, matvec.h:517) write to trash too: no predicates on the gathers and scatters
           double ein[N], eout[N], par[N];
 #pragma unroll
-          for (int r = 0; r < N; r++) par[r] = (w[N + r] == INVALID) ? 0.0 : un[w[N + r] & 0xFFFFu];
+          for (int r = 0; r < N; r++) par[r] = un[w[N + r] & 0xFFFFu];
           if (EXIP && PERM) interp_exact<N>(par);
           else tensor_interp3<DIM, M, false>(PERM ? p.ipx : p.ip, child, par);
 #pragma unroll
-          for (int r = 0; r < N; r++) ein[r] = (w[r] == INVALID) ? par[r] : un[w[r] & 0xFFFFu];
+          for (int r = 0; r < N; r++)
+          {
+            const double own = un[w[r] & 0xFFFFu];
+            ein[r] = ((fm >> r) & 1u) ? own : par[r];
+          }
           apply_op3<DIM, ORDER, OPKIND>(p, lev, ein, eout);
 #pragma unroll
           for (int r = 0; r < N; r++)
           {
-            if (w[r] != INVALID)
-            {
-              X[w[r] >> 16] = eout[r];
-              eout[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
-            }
+            X[w[r] >> 16] = eout[r];
+            if ((fm >> r) & 1u) eout[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
           }
           if (EXIP && PERM) interp_exact_T<N>(eout);
           else tensor_interp3<DIM, M, true>(PERM ? p.ipx : p.ip, child, eout);
 #pragma unroll
-          for (int q = 0; q < N; q++)
-          {
-            if (w[N + q] == INVALID) continue;
-            // Q1 (matvec.h:517): parent rank q is skipped when the LEAF's rank q is filled
-            X[w[N + q] >> 16] = (p.q1mask && w[q] != INVALID) ? 0.0 : eout[q];
-          }
+          for (int q = 0; q < N; q++) X[w[N + q] >> 16] = eout[q];
         }
       }
     }
     // T3: start the next chunk's gather and index loads; they land during T4
     if (hasN)
     {
-      issue_gather(unb + (buf ^ 1) * p.ncap, gidN, metaN);
+      issue_gather(unb + (buf ^ 1) * p.ncap, gidN, metaN, (int)(offNB - offNA));
       int *jdn = jdb + (buf ^ 1) * p.jdStride;
       for (int k = tid; k < (int)p.jdStride; k += TPB) jdn[k] = p.jd[cn * (uint64_t)p.jdStride + k];
       load_slots(cn);
@@ -758,7 +831,7 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
     {
       const int n = tid + k * TPB;
       const int len = metaC[k] & META_LEN;
-      if (len == 0) continue;
+      if (len == 0) continue;  // absent, or only read by this chunk
       double acc = X[n];  // jd[0] == 0
       for (int j = 1; j < len; j++) acc += X[jd[j] + n];
       if (DIRI && (metaC[k] & META_BDY)) continue;
@@ -782,8 +855,8 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   p.slot = cs.d_slot; p.gid = cs.d_gid; p.meta = cs.d_meta; p.jd = cs.d_jd; p.node_off = cs.d_node_off;
-  p.lev = lev; p.child = child; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
-  p.xcap = (uint32_t)rows_per_chunk(N) * N + 256u;  // + padding of the first 16 diagonals
+  p.lev = lev; p.child = child; p.fmask = da.d_fmask; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
+  p.xcap = (uint32_t)rows_per_chunk(N) * N + 258u;  // + padding of the first 16 diagonals + the trash position
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
   const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.jdStride * sizeof(int);

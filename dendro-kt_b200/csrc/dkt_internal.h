@@ -74,6 +74,7 @@ struct DA
   uint32_t *d_pnode = nullptr;     // [nHang*N]
   uint8_t *d_child = nullptr;      // [nHang]
   uint8_t *d_mv_child = nullptr;   // [nMv] Morton child number of every visited element
+  uint32_t *d_fmask = nullptr;     // [nHang] filled own slots of every hanging element (slot order)
 
   // coordinate -> node lookup: sorted unique packed keys of all lattice locations
   uint64_t *d_ukey = nullptr;      // [nU]
