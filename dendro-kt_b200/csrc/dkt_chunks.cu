@@ -67,6 +67,12 @@ constexpr uint32_t META_SHARED = 0x8000u;
 #ifndef DKT_ROWS
 #define DKT_ROWS 256
 #endif
+#ifndef DKT_REG_MINB
+#define DKT_REG_MINB 3   // resident CTAs per SM the regular kernel is compiled for (register budget)
+#endif
+#ifndef DKT_HANG_MINB
+#define DKT_HANG_MINB 4
+#endif
 int rows_per_chunk(int N)
 {
   int r = std::min(SLOT_CAP / N, DKT_ROWS);
@@ -647,7 +653,7 @@ __device__ __forceinline__ void xor_unpermute(T *v, int c)
 // the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
 // work in permuted coordinates throughout; the dense path un-permutes the slot words first.
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
-__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? 4 : 3) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
+__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? DKT_HANG_MINB : DKT_REG_MINB) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int M = ORDER + 1;
@@ -831,9 +837,18 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
     {
       const int n = tid + k * TPB;
       const int len = metaC[k] & META_LEN;
+#ifdef DKT_PHASED_UNIFORM
+      // warp-uniform trip count (nodes are sorted by run length, so lanes differ by little)
+      const int lmax = __reduce_max_sync(0xffffffffu, len);
+      double acc = 0.0;
+      for (int j = 0; j < lmax; j++)
+        if (j < len) acc += X[jd[j] + n];
+      if (len == 0) continue;
+#else
       if (len == 0) continue;  // absent, or only read by this chunk
       double acc = X[n];  // jd[0] == 0
       for (int j = 1; j < len; j++) acc += X[jd[j] + n];
+#endif
       if (DIRI && (metaC[k] & META_BDY)) continue;
       if (metaC[k] & META_SHARED) atomicAdd(p.out + gidC[k], acc);
       else p.out[gidC[k]] = acc;
