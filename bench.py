@@ -182,11 +182,11 @@ def run_gpu(args):
     v = torch.empty_like(u)
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         da.matvec(op, u, v, ghosted=ghosted)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = dkt.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -196,7 +196,15 @@ def run_gpu(args):
         ev[i + 1].record(stream)
     barrier()
     launches = dkt.kernel_launch_count() - launches0
+    my_ms = ev[0].elapsed_time(ev[-1]) / args.steps
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    per_rank = None
+    if dist is not None:  # per-rank step time and work, to see partition imbalance
+        t = torch.tensor([my_ms, float(da.n_mv_elem), float(da.n_hanging), float(da.n_nodes), float(da.n_ghost_nodes)],
+                         dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[round(float(x), 4) for x in r] for r in allt]
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     ms = total_ms / args.steps
     value = n_global / (ms * 1e-3)
@@ -251,6 +259,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "ms_per_step_min_max_rank0": [min(per_step), max(per_step)],
+            "per_rank_ms_elems_hanging_owned_ghost": per_rank,
         }
         if args.cpu_baseline and world == 1:
             try:

@@ -319,11 +319,13 @@ extern "C"
   int dkt_da_chunk_info(const dkt_da *da, uint64_t out[10])
   {
     if (!da || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
-    const ChunkSet *cs[2] = {&da->d.reg, &da->d.hang};
-    for (int i = 0; i < 2; i++)
+    // aggregated over the regular sets (out[0..4]) and the hanging sets (out[5..9])
+    for (int i = 0; i < 10; i++) out[i] = 0;
+    for (const ChunkSet &cs : da->d.sets)
     {
-      out[5 * i + 0] = cs[i]->nChunks; out[5 * i + 1] = cs[i]->elemsPerChunk; out[5 * i + 2] = cs[i]->maxNloc;
-      out[5 * i + 3] = cs[i]->maxLen; out[5 * i + 4] = cs[i]->totalNodes;
+      uint64_t *o = out + (cs.rows == 1 ? 0 : 5);
+      o[0] += cs.nChunks; o[1] = cs.elemsPerChunk; o[2] = std::max<uint64_t>(o[2], cs.maxNloc);
+      o[3] = std::max<uint64_t>(o[3], cs.maxLen); o[4] += cs.totalNodes;
     }
     return DKT_OK;
   }

@@ -340,10 +340,13 @@ __global__ void k_max_u32(const uint32_t *in, uint64_t n, uint32_t *out)
   if ((threadIdx.x & 31) == 0) atomicMax(out, v);
 }
 
-static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int rows, const uint32_t *refcnt)
+static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t hang0, uint64_t nSet, int rows, int phase, const uint32_t *refcnt)
 {
   cs = ChunkSet();
   cs.rows = rows;
+  cs.phase = phase;
+  cs.elem0 = elem0;
+  cs.hang0 = hang0;
   cs.nElem = nSet;
   if (nSet == 0) return DKT_OK;
   const int N = da.N;
@@ -357,7 +360,7 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
   CK(cudaMalloc((void **)&off, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
   const int xorperm = da.order == 1 ? 1 : 0;
   cs.xorperm = xorperm;
-  k_chunk_build<false><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
+  k_chunk_build<false><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode + hang0 * N, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
                                                                     xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
                                                                     da.d_node_isbdy, nullptr, 0, nloc, mlen, nullptr, nullptr, nullptr,
                                                                     nullptr);
@@ -387,7 +390,7 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t nSet, int ro
   CK(cudaMalloc((void **)&cs.d_gid, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&cs.d_meta, std::max<uint64_t>(total, 1) * sizeof(uint16_t)));
   CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * sizeof(uint16_t)));
-  k_chunk_build<true><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
+  k_chunk_build<true><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode + hang0 * N, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
                                                                    xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
                                                                    da.d_node_isbdy, off, (int)cs.jdStride, nullptr, nullptr, cs.d_slot,
                                                                    cs.d_gid, cs.d_meta, cs.d_jd);
@@ -407,11 +410,11 @@ void free_chunks(DA &da)
   cudaFree(da.d_fmask);
   da.d_mv_child = nullptr;
   da.d_fmask = nullptr;
-  for (ChunkSet *cs : {&da.reg, &da.hang})
+  for (ChunkSet &cs : da.sets)
   {
-    cudaFree(cs->d_slot); cudaFree(cs->d_gid); cudaFree(cs->d_meta); cudaFree(cs->d_jd); cudaFree(cs->d_node_off);
-    *cs = ChunkSet();
+    cudaFree(cs.d_slot); cudaFree(cs.d_gid); cudaFree(cs.d_meta); cudaFree(cs.d_jd); cudaFree(cs.d_node_off);
   }
+  da.sets.clear();
 }
 
 __global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_t n, int dim, int max_depth, uint8_t *child)
@@ -443,8 +446,34 @@ int build_chunks(DA &da)
                                                                        da.N, da.order == 1 ? 1 : 0, da.d_fmask);
     g_launches += 2;
   }
-  int rc = build_set(da, da.reg, 0, da.nReg, 1, refcnt);
-  if (rc == DKT_OK) rc = build_set(da, da.hang, da.nReg, da.nHang, 2, refcnt);
+  // element ranges: one regular + one hanging set, or (partitioned) three phases of each:
+  // interior first half / boundary / interior second half - see run_matvec_dist
+  struct Range { uint64_t a, b; int phase; };
+  std::vector<Range> rr, hr;
+  if (da.phased)
+  {
+    const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
+    rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
+    hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
+  }
+  else
+  {
+    rr = {{0, da.nReg, 0}};
+    hr = {{0, da.nHang, 0}};
+  }
+  int rc = DKT_OK;
+  for (const Range &r : rr)
+  {
+    if (rc != DKT_OK || r.b <= r.a) continue;
+    da.sets.emplace_back();
+    rc = build_set(da, da.sets.back(), r.a, 0, r.b - r.a, 1, r.phase, refcnt);
+  }
+  for (const Range &r : hr)
+  {
+    if (rc != DKT_OK || r.b <= r.a) continue;
+    da.sets.emplace_back();
+    rc = build_set(da, da.sets.back(), da.nReg + r.a, r.a, r.b - r.a, 2, r.phase, refcnt);
+  }
   cudaFree(refcnt);
   int dev = 0;
   CK(cudaGetDevice(&dev));
@@ -870,7 +899,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   p.slot = cs.d_slot; p.gid = cs.d_gid; p.meta = cs.d_meta; p.jd = cs.d_jd; p.node_off = cs.d_node_off;
-  p.lev = lev; p.child = child; p.fmask = da.d_fmask; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
+  p.lev = lev; p.child = child; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
   p.xcap = (uint32_t)rows_per_chunk(N) * N + 258u;  // + padding of the first 16 diagonals + the trash position
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
@@ -887,28 +916,30 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
 }
 
 template <int DIM, int ORDER, int OPKIND, bool DIRI>
-static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p)
+static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int TPB_R = (N == 27) ? 160 : DKT_ROWS;  // >= elements per chunk (one element per thread)
   constexpr int TPB_H = (N == 27) ? 96 : DKT_ROWS / 2;
-  int rc = DKT_OK;
-  if (da.reg.nChunks)
+  constexpr bool CAN_EXIP = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
+  const bool exip = CAN_EXIP && p.exact_ip;
+  for (const ChunkSet &cs : da.sets)
   {
-    if (da.reg.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, da.reg, p, da.d_mv_lev, da.d_mv_child);
-    if (rc) return rc;
-  }
-  if (da.hang.nChunks)
-  {
-    constexpr bool CAN_EXIP = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
-    const bool exip = CAN_EXIP && p.exact_ip;
-    if (da.hang.maxNloc <= 8u * TPB_H)
+    if (!cs.nChunks || !((phaseMask >> cs.phase) & 1u)) continue;
+    const uint8_t *lev = da.d_mv_lev + cs.elem0, *child = da.d_mv_child + cs.elem0;
+    p.fmask = da.d_fmask ? da.d_fmask + cs.hang0 : nullptr;
+    int rc = DKT_OK;
+    if (cs.rows == 1)
     {
-      if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
-      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+      if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p, lev, child);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, cs, p, lev, child);
     }
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, da.hang, p, da.d_mv_lev + da.nReg, da.d_mv_child + da.nReg);
+    else if (cs.maxNloc <= 8u * TPB_H)
+    {
+      if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, cs, p, lev, child);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, cs, p, lev, child);
+    }
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, cs, p, lev, child);
     if (rc) return rc;
   }
   CK(cudaGetLastError());
@@ -916,7 +947,8 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p)
 }
 
 template <int DIM, int ORDER>
-static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
+static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags, unsigned phaseMask,
+                      bool zeroOut)
 {
   using P = Mv3Params<DIM, ORDER>;
   static P p;
@@ -975,32 +1007,36 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
       }
     }
   }
-  CK(cudaMemsetAsync(d_out, 0, da.nNodes * sizeof(double), da.stream));
-  g_launches++;
+  if (zeroOut)
+  {
+    CK(cudaMemsetAsync(d_out, 0, da.nNodes * sizeof(double), da.stream));
+    g_launches++;
+  }
   const bool diri = op->dirichlet != 0;
   if constexpr (ORDER == 1)
   {
     if (hadamard)
-      return diri ? launch_mv3<DIM, ORDER, OP_HADAMARD, true>(da, p) : launch_mv3<DIM, ORDER, OP_HADAMARD, false>(da, p);
+      return diri ? launch_mv3<DIM, ORDER, OP_HADAMARD, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, OP_HADAMARD, false>(da, p, phaseMask);
   }
   if (op->kind == DKT_OP_IDENTITY)
-    return diri ? launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, true>(da, p) : launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, false>(da, p);
+    return diri ? launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, false>(da, p, phaseMask);
   if (op->kind == DKT_OP_DENSE)
-    return diri ? launch_mv3<DIM, ORDER, DKT_OP_DENSE, true>(da, p) : launch_mv3<DIM, ORDER, DKT_OP_DENSE, false>(da, p);
+    return diri ? launch_mv3<DIM, ORDER, DKT_OP_DENSE, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_DENSE, false>(da, p, phaseMask);
   set_error("unknown operator kind");
   return DKT_ERR_INVALID;
 }
 
-int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
+int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags, unsigned phaseMask,
+                       bool zeroOut)
 {
   const int key = da.dim * 10 + da.order;
   switch (key)
   {
-  case 21: return run_typed3<2, 1>(da, op, d_in, d_out, scale, flags);
-  case 22: return run_typed3<2, 2>(da, op, d_in, d_out, scale, flags);
-  case 31: return run_typed3<3, 1>(da, op, d_in, d_out, scale, flags);
-  case 32: return run_typed3<3, 2>(da, op, d_in, d_out, scale, flags);
-  case 41: return run_typed3<4, 1>(da, op, d_in, d_out, scale, flags);
+  case 21: return run_typed3<2, 1>(da, op, d_in, d_out, scale, flags, phaseMask, zeroOut);
+  case 22: return run_typed3<2, 2>(da, op, d_in, d_out, scale, flags, phaseMask, zeroOut);
+  case 31: return run_typed3<3, 1>(da, op, d_in, d_out, scale, flags, phaseMask, zeroOut);
+  case 32: return run_typed3<3, 2>(da, op, d_in, d_out, scale, flags, phaseMask, zeroOut);
+  case 41: return run_typed3<4, 1>(da, op, d_in, d_out, scale, flags, phaseMask, zeroOut);
   default:
     set_error("unsupported (dim, order)");
     return DKT_ERR_UNSUPPORTED;

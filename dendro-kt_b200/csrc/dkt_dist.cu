@@ -198,6 +198,38 @@ __global__ void k_lower_bound64(const uint64_t *a, uint64_t n, uint64_t key, uin
   }
   *out = lo;
 }
+// boundary element = touches a ghost node (local id >= nOwned) through its lattice or parent-lattice slots
+__global__ void k_is_boundary(const uint32_t *e2n, const uint32_t *pnode, uint64_t n, int N, uint32_t nOwned, uint8_t *flag)
+{
+  uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  bool b = false;
+  for (int r = 0; r < N; r++)
+  {
+    const uint32_t a = e2n[e * N + r];
+    b |= (a != INVALID && a >= nOwned);
+    if (pnode)
+    {
+      const uint32_t q = pnode[e * N + r];
+      b |= (q != INVALID && q >= nOwned);
+    }
+  }
+  flag[e] = b ? 1 : 0;
+}
+// stable partition destination: interior elements first, boundary elements after
+__global__ void k_partition_dst(const uint8_t *flag, const uint64_t *bpos, uint64_t n, uint64_t nInterior, uint32_t *dst)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (uint32_t)(flag[i] ? nInterior + bpos[i] : i - bpos[i]);
+}
+template <typename T>
+__global__ void k_permute_rows(const T *in, const uint32_t *dst, uint64_t n, int width, T *out)
+{
+  uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const uint64_t i = t / width;
+  out[(uint64_t)dst[i] * width + t % width] = in[t];
+}
 __global__ void k_pack(const double *v, const uint32_t *idx, uint64_t n, double *buf)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -244,6 +276,9 @@ int dist_allreduce(Dist &d, double *red, cudaStream_t s)
 void free_dist(Dist &d)
 {
   if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)d.comm);
+  for (int i = 0; i < 4; i++)
+    if (d.ev[i]) cudaEventDestroy(d.ev[i]);
+  if (d.comm_stream) cudaStreamDestroy(d.comm_stream);
   cudaFree(d.d_send_idx); cudaFree(d.d_send_buf); cudaFree(d.d_recv_buf); cudaFree(d.d_in_local); cudaFree(d.d_out_local);
   cudaFree(d.d_owned_gid);
   d = Dist();
@@ -263,11 +298,11 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   dist.nGlobalNodes = nNodes;
   dist.nGlobalElems = g.nElem;
   // ---- SFC-contiguous ranges of equal WEIGHT: a hanging element (two slot rows, interpolation both
-  //      ways) costs about as much as HANG_WEIGHT/REG_WEIGHT regular ones in the chunked kernels
+  //      ways) costs HANG_WEIGHT/REG_WEIGHT regular ones in the chunked kernels
   Bounds B;
   B.nranks = nranks;
   {
-    constexpr uint64_t REG_WEIGHT = 4, HANG_WEIGHT = 9;
+    constexpr uint64_t REG_WEIGHT = 3, HANG_WEIGHT = 5;  // measured: 45 vs 75 ns per element (profiles/)
     uint64_t *wsrc = nullptr, *wscan = nullptr, *dbound = nullptr;
     CK(cudaMalloc((void **)&wsrc, (nMv + 1) * sizeof(uint64_t)));
     CK(cudaMalloc((void **)&wscan, (nMv + 1) * sizeof(uint64_t)));
@@ -407,6 +442,67 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
 
+  // ---- [interior | boundary] order inside the regular and the hanging list, so that interior elements can
+  //      run while the ghost exchanges are in flight --------------------------------------------------------------
+  // Measured on 8 B200s (profiles/README.md): the split pays at 8 ranks (0.95 vs 1.00 ms) and costs at 2
+  // (three kernel pairs instead of one); default: on for more than 2 ranks, DKT_DIST_OVERLAP=0/1 overrides.
+  bool wantOverlap = nranks > 2;
+  if (const char *e = getenv("DKT_DIST_OVERLAP")) wantOverlap = atoi(e) != 0;
+  uint64_t nRegInt = nRegL, nHangInt = nHangL;
+  for (int pass = 0; pass < 2 && wantOverlap; pass++)
+  {
+    const uint64_t cnt = pass == 0 ? nRegL : nHangL, first = pass == 0 ? 0 : nRegL;
+    if (cnt == 0) continue;
+    uint8_t *bflag = nullptr;
+    uint64_t *bw = nullptr, *bp = nullptr;
+    uint32_t *dst = nullptr;
+    CK(cudaMalloc((void **)&bflag, cnt));
+    CK(cudaMalloc((void **)&bw, (cnt + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&bp, (cnt + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&dst, cnt * sizeof(uint32_t)));
+    LAUNCHS(k_is_boundary, cnt, g.stream, e2nL + first * N, pass == 0 ? (const uint32_t *)nullptr : (const uint32_t *)pnodeL, cnt, N,
+            (uint32_t)nOwned, bflag);
+    uint64_t nB = 0;
+    rc = positions(g, bflag, cnt, bw, bp, nB);
+    if (rc) return rc;
+    const uint64_t nI = cnt - nB;
+    LAUNCHS(k_partition_dst, cnt, g.stream, bflag, bp, cnt, nI, dst);
+    auto permute32 = [&](uint32_t *&arr, uint64_t off, int width) -> int {
+      uint32_t *tmp = nullptr;
+      CK(cudaMalloc((void **)&tmp, cnt * width * sizeof(uint32_t)));
+      LAUNCHS(k_permute_rows<uint32_t>, cnt * width, g.stream, arr + off * width, dst, cnt, width, tmp);
+      CK(cudaMemcpyAsync(arr + off * width, tmp, cnt * width * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+      CK(cudaStreamSynchronize(g.stream));
+      cudaFree(tmp);
+      return DKT_OK;
+    };
+    auto permute8 = [&](uint8_t *&arr, uint64_t off) -> int {
+      uint8_t *tmp = nullptr;
+      CK(cudaMalloc((void **)&tmp, cnt));
+      LAUNCHS(k_permute_rows<uint8_t>, cnt, g.stream, arr + off, dst, cnt, 1, tmp);
+      CK(cudaMemcpyAsync(arr + off, tmp, cnt, cudaMemcpyDeviceToDevice, g.stream));
+      CK(cudaStreamSynchronize(g.stream));
+      cudaFree(tmp);
+      return DKT_OK;
+    };
+    if ((rc = permute32(e2nL, first, N))) return rc;
+    if ((rc = permute32(xyzL, first, dim))) return rc;
+    if ((rc = permute32(srcL, first, 1))) return rc;
+    if ((rc = permute8(levL, first))) return rc;
+    if (pass == 1)
+    {
+      if ((rc = permute32(pnodeL, 0, N))) return rc;
+      if ((rc = permute8(childL, 0))) return rc;
+      nHangInt = nI;
+    }
+    else
+      nRegInt = nI;
+    cudaFree(bflag); cudaFree(bw); cudaFree(bp); cudaFree(dst);
+  }
+  g.phased = wantOverlap;
+  g.nRegInterior = nRegInt;
+  g.nHangInterior = nHangInt;
+
   // ---- swap the global tables for the local ones -------------------------------------------------------------------
   cudaFree(g.d_e2n); cudaFree(g.d_pnode); cudaFree(g.d_mv_xyz); cudaFree(g.d_mv_src); cudaFree(g.d_mv_lev); cudaFree(g.d_child);
   cudaFree(g.d_node_isbdy); cudaFree(g.d_ukey); cudaFree(g.d_unode);
@@ -426,6 +522,8 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
     NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
     dist.comm = comm;
   }
+  CK(cudaStreamCreateWithFlags(&dist.comm_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&dist.ev[i], cudaEventDisableTiming));
   dist.active = true;
   return DKT_OK;
 }
@@ -442,37 +540,68 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
   double *in_local = ghosted ? const_cast<double *>(d_in) : d.d_in_local;
   double *out_local = ghosted ? d_out : d.d_out_local;
   if (!ghosted) CK(cudaMemcpyAsync(in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  const bool overlap = d.nranks > 1 && da.phased && !(flags & DKT_MV_FLAT);
+  cudaStream_t cs = overlap ? d.comm_stream : s;  // the exchanges run beside the interior elements
   if (d.nranks > 1)
   {
     // readFromGhost: owners -> ghosts, received straight into the ghost segments of the local vector
     LAUNCHS(k_pack, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_buf);
+    if (overlap)
+    {
+      CK(cudaEventRecord(d.ev[0], s));
+      CK(cudaStreamWaitEvent(cs, d.ev[0], 0));
+    }
     NCK(g_nccl.GroupStart());
     for (int p = 0; p < d.nranks; p++)
     {
       if (p == d.rank) continue;
       const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
-      if (sc) NCK(g_nccl.Send(d.d_send_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
-      if (rcv) NCK(g_nccl.Recv(in_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (sc) NCK(g_nccl.Send(d.d_send_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+      if (rcv) NCK(g_nccl.Recv(in_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
     }
     NCK(g_nccl.GroupEnd());
     g_launches++;
+    if (overlap) CK(cudaEventRecord(d.ev[1], cs));
   }
-  int rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
-                                 : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
-  if (rc) return rc;
+  int rc = DKT_OK;
+  if (!overlap)
+  {
+    rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
+                               : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
+    if (rc) return rc;
+  }
+  else
+  {
+    // interior elements (first half) touch no ghost node: they run while the ghost values arrive
+    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, d.ev[1], 0));
+    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
+    if (rc) return rc;
+    CK(cudaEventRecord(d.ev[2], s));
+    CK(cudaStreamWaitEvent(cs, d.ev[2], 0));
+  }
   if (d.nranks > 1)
   {
-    // writeToGhosts: ghost partial sums -> owners, accumulated
+    // writeToGhosts: ghost partial sums (complete after the boundary elements) -> owners, accumulated
     NCK(g_nccl.GroupStart());
     for (int p = 0; p < d.nranks; p++)
     {
       if (p == d.rank) continue;
       const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
-      if (rcv) NCK(g_nccl.Send(out_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
-      if (sc) NCK(g_nccl.Recv(d.d_recv_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, s));
+      if (rcv) NCK(g_nccl.Send(out_local + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+      if (sc) NCK(g_nccl.Recv(d.d_recv_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
     }
     NCK(g_nccl.GroupEnd());
     g_launches++;
+    if (overlap)
+    {
+      CK(cudaEventRecord(d.ev[3], cs));
+      // interior elements (second half) run while the partial sums travel
+      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);
+      if (rc) return rc;
+      CK(cudaStreamWaitEvent(s, d.ev[3], 0));
+    }
     LAUNCHS(k_unpack_add, totalSend, s, out_local, d.d_send_idx, totalSend, d.d_recv_buf);
   }
   if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));

@@ -35,6 +35,9 @@ extern uint64_t g_launches;
 struct ChunkSet
 {
   int rows = 1;                  // slot rows per element: 1 regular, 2 hanging (own + parent lattice)
+  int phase = 0;                 // partitioned DA: 0 interior (first half), 1 boundary, 2 interior (second half)
+  uint64_t elem0 = 0;            // first visited element of the set (index into d_mv_*, d_e2n)
+  uint64_t hang0 = 0;            // hanging sets: first hanging-local element (index into d_pnode, d_fmask)
   int xorperm = 0;               // slot s of an element with child number c holds rank s ^ c (order 1)
   uint64_t nElem = 0;
   uint32_t nChunks = 0, elemsPerChunk = 0, maxNloc = 0, maxLen = 0, jdStride = 0;
@@ -82,7 +85,10 @@ struct DA
 
   double ip[2][MAX_M * MAX_M];     // parent->child 1-D matrices, A[k*M+j]
 
-  ChunkSet reg, hang;              // chunked tables of elements [0,nReg) and [nReg,nMv)
+  std::vector<ChunkSet> sets;      // chunked tables; single rank: {regular, hanging}; partitioned: x3 phases
+  // partitioned DA: regular elements are ordered [interior | boundary], boundary = touches a ghost node
+  uint64_t nRegInterior = 0, nHangInterior = 0;
+  bool phased = false;
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
@@ -97,6 +103,8 @@ struct Dist
   bool active = false;
   int rank = 0, nranks = 1;
   void *comm = nullptr;                 // ncclComm_t
+  cudaStream_t comm_stream = nullptr;   // the exchanges run here, overlapped with interior elements
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t nOwned = 0, nGhost = 0, nGlobalNodes = 0, nGlobalElems = 0;
   std::vector<uint64_t> send_off, recv_off;  // [nranks+1] offsets into the send list / the ghost segment
   uint32_t *d_send_idx = nullptr;       // local ids of owned nodes other ranks ghost, grouped by peer
@@ -118,7 +126,8 @@ void free_da(DA &da);
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
 int build_chunks(DA &da);
 void free_chunks(DA &da);
-int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags,
+                       unsigned phaseMask = 7u, bool zeroOut = true);
 int device_exclusive_scan(DA &da, const uint64_t *in, uint64_t *out, uint64_t n);
 } // namespace dkt
 
