@@ -597,6 +597,9 @@ int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t
   CK(cudaEventCreate(&da.ev0));
   CK(cudaEventCreate(&da.ev1));
   if (n == 0) { set_error("empty tree"); return DKT_ERR_INVALID; }
+  // device-resident input may still be in flight on a stream of the caller's (e.g. torch's current stream);
+  // construction is a one-off, so simply wait for the device
+  if (flags & DKT_ELEMS_ON_DEVICE) CK(cudaDeviceSynchronize());
   if (n * (uint64_t)da.N >= 0xFFFFFFFFull) { set_error("n_elem * nodes_per_elem must be < 2^32"); return DKT_ERR_UNSUPPORTED; }
 
   SfcTables tab;

@@ -145,7 +145,9 @@ int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, ui
 
 /* Replaces feMatrix<LeafT,dim>::matVec(const VECType*in, VECType*out, double scale)
  * (FEM/include/feMatrix.h:190-259) including fem::matvec (FEM/include/matvec.h:232) for one
- * rank.  in/out have n_nodes doubles in DA order. */
+ * rank.  in/out have n_nodes doubles in DA order.  Device vectors: the kernels are enqueued on the DA's
+ * stream (dkt_da_stream / dkt_da_set_stream) and the call returns without waiting; the caller orders that
+ * stream after the producer of `in` and before the consumer of `out`. */
 int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags);
 
 /* Conjugate gradients with every vector resident in HBM: the solver of the reference's example
