@@ -249,7 +249,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # ncu dram__bytes_read+write of the step's kernels on the default workload (profiles/README.md);
                          # None for other workloads
-                         "traffic": 1.767e9 if (world == 1 and level == 9 and args.per_gpu_elems == 1.2e7) else None,
+                         "traffic": 1.78e9 if (world == 1 and level == 9 and args.per_gpu_elems == 1.2e7) else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                          "alg_bytes_per_step_per_gpu": alg_total / world,
                          "kernel": "whole matvec step per GPU (memset + chunked regular + hanging kernels" +
