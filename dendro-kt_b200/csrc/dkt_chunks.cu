@@ -909,7 +909,12 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
   int perSM = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TPB, smem));
   if (perSM < 1) { set_error("chunk kernel does not fit on an SM"); return DKT_ERR_CUDA; }
-  const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * da.numSMs));
+  // Persistent CTAs normally fill every SM.  While a ghost exchange is in flight (partitioned DA, interior
+  // phases) a few SMs are left free, otherwise the NCCL kernels could not start before this one ends and
+  // nothing would overlap.
+  int sms = da.numSMs;
+  if (da.phased && cs.phase != 1) sms = std::max(1, da.numSMs - da.commSMs);
+  const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * sms));
   kern<<<grid, TPB, smem, da.stream>>>(p);
   g_launches++;
   return DKT_OK;

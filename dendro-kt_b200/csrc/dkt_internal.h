@@ -89,6 +89,7 @@ struct DA
   // partitioned DA: regular elements are ordered [interior | boundary], boundary = touches a ghost node
   uint64_t nRegInterior = 0, nHangInterior = 0;
   bool phased = false;
+  int commSMs = 0;                 // SMs left to the NCCL kernels during the interior phases
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
