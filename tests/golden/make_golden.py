@@ -62,7 +62,46 @@ def generate(case):
     return out
 
 
+def generate_heatmat(name):
+    """The reference's own example operator, HeatEq::HeatMat<3> (FEM/examples/src/heatMat.cpp:46-139):
+    v = A u through feMatrix::matVec with its Dirichlet pre/postMatVec, plus the reference-cell matrix
+    recovered by probing HeatMat<3>::elementalMatVec with unit vectors on cells of two levels."""
+    case = cases.make_case(name)
+    R = dktref.Reference(3, case["max_depth"], "morton")
+    tree = R.tree_from_elements(case["xyz"], case["lev"], sort=True)
+    da = R.da(tree, 1)
+    n = da.num_nodes
+    u = cases.input_vector(n)
+    v_heat, _, _ = da.matvec(u, dktref.OP_HEATMAT)
+    mi = np.array([[(r >> d) & 1 for d in range(3)] for r in range(8)], dtype=np.float64)
+
+    def probe(level):
+        h = 2.0 ** -level
+        K = np.zeros((8, 8))
+        for j in range(8):
+            e = np.zeros(8)
+            e[j] = 1.0
+            K[:, j] = da.heat_elemental(e, (mi * h).ravel())
+        return K
+    K2, K3 = probe(2), probe(3)
+    alpha = float(np.log2(K2[0, 0] / K3[0, 0]))
+    assert np.abs(K3 - K2 * 2.0 ** -alpha).max() <= 1e-13 * np.abs(K3).max()
+    re = R.refel(1)
+    return dict(dim=3, order=1, max_depth=case["max_depth"], in_xyz=case["xyz"], in_lev=case["lev"], ip0=re["ip0"], ip1=re["ip1"],
+                v_heat=v_heat, heat_kref=K2 * 2.0 ** (alpha * 2), heat_alpha=alpha, node_xyz=da.nodes()[0])
+
+
+HEATMAT_CASES = {"heatmat-d3-p1-ball": "ball-d3-p1-morton-6", "heatmat-d3-p1-ex3": "ex3-d3-p1-morton-3"}
+
+
 def main():
+    for fixture, name in HEATMAT_CASES.items():
+        g = generate_heatmat(name)
+        path = os.path.join(HERE, fixture + ".npz")
+        np.savez_compressed(path, **g)
+        print("%-28s nN=%6d alpha=%.3f  %6.1f KB" % (fixture, len(g["v_heat"]), g["heat_alpha"], os.path.getsize(path) / 1024))
+    if "--heatmat-only" in sys.argv:
+        return
     for name in cases.ALL_CASES:
         case = point_cloud_case(name) if name in cases.POINT_CLOUD_CASES else cases.make_case(name)
         g = generate(case)

@@ -93,6 +93,22 @@ def test_structured_operator_fast_path(dkt, name):
     da.close()
 
 
+@pytest.mark.parametrize("fixture", ["heatmat-d3-p1-ball", "heatmat-d3-p1-ex3"])
+def test_reference_heatmat_operator(dkt, fixture):
+    """v = A u of the reference's own HeatEq::HeatMat<3> (stiffness operator + Dirichlet pre/postMatVec,
+    FEM/examples/src/heatMat.cpp:46-139) against the device operator built from its probed K_ref, and
+    against the library's own unit-cube Laplacian."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture + ".npz")))
+    da = dkt.DA(g["in_xyz"], g["in_lev"], 3, 1, int(g["max_depth"]), ip0=g["ip0"], ip1=g["ip1"])
+    u = cases.input_vector(da.n_nodes)
+    for K in (g["heat_kref"], dkt.operators.laplace_kref(3, 1)):
+        for kw in (dict(), dict(fastpath=False), dict(flat=True)):
+            v = da.matvec(dkt.Operator.dense(K, float(g["heat_alpha"]), dirichlet=True), u, **kw)
+            assert np.abs(v - g["v_heat"]).max() <= TOL * np.abs(g["v_heat"]).max()
+    da.close()
+
+
 def test_device_pointer_path_and_repeatability(dkt):
     import torch
     dim, md = 3, 12

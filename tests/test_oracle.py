@@ -109,3 +109,20 @@ def test_oracle_against_live_reference():
     vo = flat.matvec(t, u, K, alpha=dim - 2.0, ip0=re["ip0"], ip1=re["ip1"])
     assert ncalls == len(t.mv_lev)
     assert np.abs(vr - vo).max() <= 1e-13 * np.abs(vr).max()
+
+
+@pytest.mark.parametrize("fixture", ["heatmat-d3-p1-ball", "heatmat-d3-p1-ex3"])
+def test_reference_heatmat_operator(fixture):
+    """The reference's own example operator HeatEq::HeatMat<3> (FEM/examples/src/heatMat.cpp:46-139):
+    its elemental operator is h^1 * K_ref on axis-aligned cells; the flat matvec with the probed K_ref and
+    Dirichlet rows reproduces feMatrix::matVec of the reference, and K_ref is the unit-cube Laplacian."""
+    import dkt
+    g = dict(np.load(os.path.join(GOLDEN, fixture + ".npz")))
+    t = flat.build_tables(g["in_xyz"], g["in_lev"], 3, 1, int(g["max_depth"]))
+    assert np.array_equal(t.node_xyz, g["node_xyz"])
+    assert abs(float(g["heat_alpha"]) - 1.0) < 1e-12
+    u = cases.input_vector(len(t.node_lev))
+    v = flat.matvec(t, u, g["heat_kref"], alpha=float(g["heat_alpha"]), ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
+    assert np.abs(v - g["v_heat"]).max() <= 1e-13 * np.abs(g["v_heat"]).max()
+    K = dkt.operators.laplace_kref(3, 1)
+    assert np.abs(K - g["heat_kref"]).max() <= 1e-13 * np.abs(K).max()
