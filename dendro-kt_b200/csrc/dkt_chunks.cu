@@ -27,10 +27,23 @@
 //         neighbouring lanes have equal len, so no divergence) and ONE plain store (node private
 //         to the chunk) or ONE fp64 RED (shared) per (chunk, node)
 //
-// Global atomics drop from N per element to ~2 per element in 4-D (the chunk surface).  Hanging
-// elements live in their own chunk set with two slot rows each (own lattice + parent lattice),
-// so neither instantiation diverges.  Semantics are those of dkt_matvec.cu (reference:
-// FEM/include/matvec.h:378-522), including quirk Q1.
+// Global atomics drop from N per element to ~2-3 per element in 4-D (the chunk surface).
+//
+// Order-1 extras (all build-time table tricks, no extra kernel work):
+//   * XOR slot schedule: slot s of an element with Morton child number c holds lattice rank s ^ c, so
+//     sibling elements read the SAME node in the same instruction (shared-memory broadcast).  The
+//     identity and Walsh-Hadamard operator forms commute with that permutation, and the parent->child
+//     interpolation becomes child-independent (exact form: subset-sum transforms).
+//   * the first 16 jagged diagonals start at positions congruent to k modulo 16, so the k-th
+//     contributions to one node written by siblings in one instruction fall into distinct bank pairs.
+// Hanging elements live in their own chunk sets with two slot rows each (own lattice + parent lattice),
+// so neither instantiation diverges, and they carry no predicates: an absent node reads the chunk's zero
+// entry un[nloc] and writes to a trash position behind the diagonals; parent slots masked by quirk Q1
+// (FEM/include/matvec.h:517) are read-only (node rank but no position, not counted in the run length);
+// one 32-bit mask per element tells which own slots are filled.  Semantics are those of dkt_matvec.cu
+// (reference: FEM/include/matvec.h:378-522); the Q1-free variant runs on the flat kernels.
+// Partitioned DAs build three phases of sets (interior first half / boundary / interior second half)
+// so that dkt_dist.cu can run the ghost exchanges beside the interior elements.
 #include "dkt_internal.h"
 
 #include <cub/block/block_radix_sort.cuh>

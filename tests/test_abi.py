@@ -91,3 +91,46 @@ def test_procedural_trees_are_balanced(dkt):
         np.maximum.at(mx, t.e2n[f], np.repeat(lv, N).reshape(-1, N)[f])
         np.minimum.at(mn, t.e2n[f], np.repeat(lv, N).reshape(-1, N)[f])
         assert (mx - mn).max() <= 1
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/dkt.h must compile as C99 with no C++ or torch types."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "dkt.h"\nint main(void){ dkt_op op; dkt_sizes s; (void)op; (void)s; return DKT_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_reference_cell_operators(dkt):
+    """Host-side operator setup: symmetric, constants in the Laplacian's null space, mass sums to the cell
+    volume, and at order 1 both are diagonal in the Walsh-Hadamard basis (the form the kernels exploit)."""
+    for dim in (2, 3, 4):
+        for order in (1, 2):
+            K, M = dkt.operators.laplace_kref(dim, order), dkt.operators.mass_kref(dim, order)
+            N = (order + 1) ** dim
+            assert K.shape == (N, N) and np.abs(K - K.T).max() < 1e-13 and np.abs(M - M.T).max() < 1e-13
+            assert np.abs(K @ np.ones(N)).max() < 1e-12 and abs(M.sum() - 1.0) < 1e-12
+            if order == 1:
+                H = np.array([[(-1.0) ** bin(i & j).count("1") for j in range(N)] for i in range(N)])
+                for A in (K, M):
+                    D = H @ A @ H / N
+                    assert np.abs(D - np.diag(np.diag(D))).max() <= 1e-13 * np.abs(D).max()
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's CPU matvec through oracle/_ref) prints the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dktref
+    if not dktref.available("morton"):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "DOF/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
