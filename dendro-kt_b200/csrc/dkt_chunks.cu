@@ -6,12 +6,13 @@
 // (profiles/r01_*).  Shared-memory fp64 atomics are CAS spin loops on sm_100a
 // (ATOMS.CAST.SPIN.64), so the in-chunk reduction is made atomic-free instead.
 //
-//   build (once per DA, k_chunk_build, one CTA per chunk, cub::BlockRadixSort in shared memory):
-//     * the chunk's slots (element, rank) are sorted by the node they touch -> unique nodes,
-//       run length `len` of each node
+//   build (once per DA): every set of UNITS (elements, or sibling groups - see below) first gets a
+//   "unit slot table" U[unit][slot] = node id (k_unit_slots_*), then k_chunk_build (one CTA per chunk,
+//   cub::BlockRadixSort in shared memory) turns it into the chunk tables:
+//     * the chunk's slots are sorted by the node they touch -> unique nodes, run length `len` of each node
 //     * nodes are re-ranked by (len descending, id ascending): jagged-diagonal storage.  The k-th
 //       contribution to node n lives at X[jd[k] + n]; jd[k] = number of (node, j<k) pairs.
-//     * every slot gets one 32-bit word  n | (jd[k] + n) << 16 ; words are stored rank-major
+//     * every slot gets one 32-bit word  n | (jd[k] + n) << 16 ; words are stored slot-major
 //       inside the chunk so that a warp reads 32 consecutive words
 //     * every node gets its global id and a meta word: len | boundary bit | shared-with-another-
 //       chunk bit (global reference count != len)
@@ -44,13 +45,30 @@
 // (reference: FEM/include/matvec.h:378-522); the Q1-free variant runs on the flat kernels.
 // Partitioned DAs build three phases of sets (interior first half / boundary / interior second half)
 // so that dkt_dist.cu can run the ghost exchanges beside the interior elements.
+//
+// SIBLING GROUPS (order 1, opt-in: environment DKT_GROUPS=g at DA construction; see k_mvg below): the
+// 2^g leaves of a complete sibling family that agree in the child-number bits of the dimensions >= g are ONE
+// unit handled by one thread.  They share a 3^g x 2^(dim-g) node lattice, so a quad (dim 4, g = 2) needs 36
+// gathers and 36 scatters where four separate elements need 64 + 64, and a hanging group reads the 16 parent
+// nodes once.  Elements outside complete families stay in per-element sets.
+//
+// This file also compiles under -DDKT_EMU with tests/emu/cuda_emu.h (fibers on the CPU) - that build exists
+// ONLY so the CPU test-suite can execute the table construction and the kernels' logic against the oracle;
+// it is never part of libdkt.so.
 #include "dkt_internal.h"
 
+#ifdef DKT_EMU
+#include "cuda_emu.h"
+#else
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
+#define DKT_LAUNCH(k, g, b, s, st) k<<<(g), (b), (s), (st)>>>
+#define DKT_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace dkt
@@ -67,13 +85,17 @@ namespace dkt
   } while (0)
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
-constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;  // 4096 slots per chunk
+constexpr int SORT_ITEMS = 16;                       // per-element sets: 4096 slots per chunk
+constexpr int SORT_ITEMS_GRP = 18;                   // sibling-group sets: 4608 slots per chunk (128 quads of 36)
+constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;
+constexpr int SLOT_CAP_GRP = SORT_THREADS * SORT_ITEMS_GRP;
 constexpr int MAX_LEN = 511;                         // run length of a node inside a chunk (9 bits)
 constexpr uint32_t META_LEN = 0x1FFu;
 constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty: only read by this chunk)
 constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
+constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
+constexpr int GRP_TPB = 128;                // threads (= units per chunk at most) of the group kernels
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
@@ -86,24 +108,27 @@ constexpr uint32_t META_SHARED = 0x8000u;
 #ifndef DKT_HANG_MINB
 #define DKT_HANG_MINB 4
 #endif
+#ifndef DKT_GRP_MINB
+#define DKT_GRP_MINB 2   // resident CTAs per SM the group kernels are compiled for
+#endif
 int rows_per_chunk(int N)
 {
   int r = std::min(SLOT_CAP / N, DKT_ROWS);
   return r & ~1;
 }
+static inline unsigned nblk(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
 // ------------------------------------------------------------------------------------------
 // build
 // ------------------------------------------------------------------------------------------
-// Number of WRITING references of every node.  Own-lattice slots always write; a parent-lattice slot q
-// of a hanging element writes only if the element's own rank q is unfilled (quirk Q1 is static in the
-// chunk tables: FEM/include/matvec.h:517) - `own` is the element's e2n row, null for the own rows.
-__global__ void k_ref_count(const uint32_t *ids, const uint32_t *own, uint64_t n, uint32_t *cnt)
+// Number of WRITING references of every node over the unit slot tables of all sets.
+__global__ void k_ref_count(const uint32_t *U, uint64_t n, uint32_t *cnt)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n || ids[i] == INVALID) return;
-  if (own && own[i] != INVALID) return;  // read-only parent slot
-  atomicAdd(cnt + ids[i], 1u);
+  if (i >= n) return;
+  const uint32_t k = U[i];
+  if (k == INVALID || (k & SLOT_RO)) return;
+  atomicAdd(cnt + k, 1u);
 }
 // bit s of fmask[h]: own slot s of hanging element h is filled (slot order, i.e. XOR-permuted at order 1)
 __global__ void k_fmask(const uint32_t *e2n_hang, const uint8_t *child_hang, uint64_t nHang, int N, int xorperm, uint32_t *fmask)
@@ -117,51 +142,80 @@ __global__ void k_fmask(const uint32_t *e2n_hang, const uint8_t *child_hang, uin
   fmask[h] = m;
 }
 
-// One CTA per chunk.  WRITE == false: only report the chunk's node count and longest run.
-template <bool WRITE>
-__global__ void __launch_bounds__(SORT_THREADS)
-k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz, const uint8_t *mv_lev, int dim, int max_depth,
-              int xorperm, uint64_t elem0, uint64_t nSet, int N, int rows, int elemsPerChunk, const uint32_t *refcnt,
-              const uint8_t *isbdy, const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out,
-              uint32_t *slot, uint32_t *gid_out, uint16_t *meta_out, uint16_t *jd_out)
+// Unit slot table of a per-element set: slot q < N holds the element's lattice rank q ^ c (c = Morton child
+// number with the XOR schedule, else 0), slots N..2N-1 (hanging sets) the parent-lattice rank (q-N) ^ c.  Own
+// slots always write; a parent slot writes only if the element's own rank is unfilled (quirk Q1 is static in
+// the chunk tables: FEM/include/matvec.h:517), otherwise it is a read-only reference.
+__global__ void k_unit_slots_elem(const uint32_t *e2n, const uint32_t *pnode, const uint8_t *child, uint64_t nUnits, int N, int rows,
+                                  int xorperm, uint32_t *U)
 {
-  using SortPairs = cub::BlockRadixSort<uint32_t, SORT_THREADS, SORT_ITEMS, uint16_t>;
-  using SortKeys = cub::BlockRadixSort<uint32_t, SORT_THREADS, SORT_ITEMS>;
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const int spu = rows * N;
+  if (i >= nUnits * spu) return;
+  const uint64_t u = i / spu;
+  const int q = (int)(i % spu);
+  const int c = xorperm ? child[u] : 0;
+  uint32_t key;
+  if (q < N) key = e2n[u * N + (q ^ c)];
+  else
+  {
+    const int r = (q - N) ^ c;
+    key = pnode[u * N + r];
+    if (key != INVALID && e2n[u * N + r] != INVALID) key |= SLOT_RO;
+  }
+  U[i] = key;
+}
+
+// One CTA per chunk of `upc` units with `spu` slots each (U is unit-major).  WRITE == false: only report the
+// chunk's node count and longest run.  split16: the slot words are stored as two 16-bit arrays (node rank /
+// position), two slots per 32-bit word, and the node records as 8-byte {gid, meta} pairs (group sets).
+template <bool WRITE, int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16, const uint32_t *refcnt, const uint8_t *isbdy,
+              const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out, uint32_t *slot, uint16_t *rk16,
+              uint16_t *ps16, uint32_t *gid_out, uint16_t *meta_out, uint2 *rec_out, uint16_t *jd_out)
+{
+  constexpr int CAP = SORT_THREADS * ITEMS;
+  using SortPairs = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS, uint16_t>;
+  using SortKeys = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS>;
   using Scan = cub::BlockScan<int, SORT_THREADS>;
   __shared__ union
   {
     typename SortPairs::TempStorage pairs;
     typename SortKeys::TempStorage keys;
     typename Scan::TempStorage scan;
-    uint16_t newrank[SLOT_CAP];                // by gid-rank: rank after the (len desc) re-sort (after the sorts)
+    uint16_t newrank[CAP];                     // by gid-rank: rank after the (len desc) re-sort (after the sorts)
   } tmp;
   uint16_t *s_newrank = tmp.newrank;
   __shared__ uint32_t s_last[SORT_THREADS];
-  __shared__ uint16_t s_start[SLOT_CAP + 1];   // by gid-rank: first sorted position of the node's references
-  __shared__ uint16_t s_cw[SLOT_CAP + 1];      // by gid-rank: number of WRITING references sorted before the node
+  __shared__ uint16_t s_start[CAP + 1];        // by gid-rank: first sorted position of the node's references
+  __shared__ uint16_t s_cw[CAP + 1];           // by gid-rank: number of WRITING references sorted before the node
   __shared__ int s_hist[MAX_LEN + 2];
   __shared__ int s_jd[MAX_LEN + 2];
   __shared__ int s_total, s_P, s_maxlen;
 
   const uint64_t c = blockIdx.x;
-  const uint64_t e0 = c * (uint64_t)elemsPerChunk;
-  const int ne = (int)min((uint64_t)elemsPerChunk, nSet - e0);
-  const int spe = rows * N;  // slots per element
-  const int nslots = ne * spe;
+  const uint64_t u0 = c * (uint64_t)upc;
+  const int nu = (int)min((uint64_t)upc, nUnits - u0);
+  const int nslots = nu * spu;
 
-  uint32_t key[SORT_ITEMS];
-  uint16_t val[SORT_ITEMS];
+  // key = node id, val = slot index inside the chunk (unit-major: unit * spu + slot) | read-only bit 15
+  uint32_t key[ITEMS];
+  uint16_t val[ITEMS];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
-    const int s = threadIdx.x * SORT_ITEMS + i;
+    const int s = threadIdx.x * ITEMS + i;
     key[i] = INVALID;
     val[i] = (uint16_t)s;
     if (s < nslots)
     {
-      const uint64_t e = e0 + s / spe;  // element index inside the set
-      const int q = s % spe;
-      key[i] = q < N ? e2n[(elem0 + e) * N + q] : pnode[e * (uint64_t)N + (q - N)];
+      const uint32_t raw = U[u0 * spu + s];
+      if (raw != INVALID)
+      {
+        key[i] = raw & ~SLOT_RO;
+        if (raw & SLOT_RO) val[i] |= 0x8000u;
+      }
     }
   }
   if (threadIdx.x == 0) { s_P = 0; s_maxlen = 0; }
@@ -169,61 +223,55 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
   SortPairs(tmp.pairs).Sort(key, val);
   __syncthreads();
   // heads: first occurrence of each node id in sorted order (invalid keys sort last)
-  s_last[threadIdx.x] = key[SORT_ITEMS - 1];
+  s_last[threadIdx.x] = key[ITEMS - 1];
   __syncthreads();
   uint32_t prev = threadIdx.x ? s_last[threadIdx.x - 1] : INVALID;
-  int head[SORT_ITEMS];
+  int head[ITEMS];
   int nheads = 0, lastvalid = 0;
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
     const bool first = (threadIdx.x == 0 && i == 0);
     head[i] = (key[i] != INVALID) && (first || key[i] != prev);
     prev = key[i];
     nheads += head[i];
-    if (key[i] != INVALID) lastvalid = threadIdx.x * SORT_ITEMS + i + 1;
+    if (key[i] != INVALID) lastvalid = threadIdx.x * ITEMS + i + 1;
   }
   int before = 0, total = 0;
   Scan(tmp.scan).ExclusiveSum(nheads, before, total);
   if (lastvalid) atomicMax(&s_P, lastvalid);
-  uint16_t rank0[SORT_ITEMS];
+  uint16_t rank0[ITEMS];
   {
     int rk = before - 1;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++)
+    for (int i = 0; i < ITEMS; i++)
     {
       if (head[i])
       {
         rk++;
-        s_start[rk] = (uint16_t)(threadIdx.x * SORT_ITEMS + i);
+        s_start[rk] = (uint16_t)(threadIdx.x * ITEMS + i);
       }
       rank0[i] = (uint16_t)(rk < 0 ? 0 : rk);
     }
   }
   if (threadIdx.x == 0) s_total = total;
-  // writing references: every valid own-lattice slot; parent-lattice slots only where the element's
-  // own rank is unfilled (static Q1).  k-th WRITING reference of a node -> diagonal k.
-  int wr[SORT_ITEMS];
+  // k-th WRITING reference of a node -> diagonal k
+  int wr[ITEMS];
   int nwr = 0;
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
-    wr[i] = 0;
-    if (key[i] != INVALID)
-    {
-      const int q = val[i] % spe, el = val[i] / spe;
-      wr[i] = (q < N) ? 1 : (e2n[(elem0 + e0 + el) * N + (q - N)] == INVALID);
-    }
+    wr[i] = (key[i] != INVALID) && !(val[i] & 0x8000u);
     nwr += wr[i];
   }
   __syncthreads();
   int wbefore = 0, wtotal = 0;
   Scan(tmp.scan).ExclusiveSum(nwr, wbefore, wtotal);
-  uint16_t cwi[SORT_ITEMS];
+  uint16_t cwi[ITEMS];
   {
     int acc = wbefore;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; i++)
+    for (int i = 0; i < ITEMS; i++)
     {
       cwi[i] = (uint16_t)acc;
       if (head[i]) s_cw[rank0[i]] = (uint16_t)acc;
@@ -239,16 +287,16 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
   }
   __syncthreads();
   // second sort: nodes by (len descending, gid-rank ascending)
-  uint32_t k2[SORT_ITEMS];
+  uint32_t k2[ITEMS];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
-    const int n = threadIdx.x * SORT_ITEMS + i;
+    const int n = threadIdx.x * ITEMS + i;
     k2[i] = INVALID;
     if (n < nloc)
     {
       const int len = (int)s_cw[n + 1] - (int)s_cw[n];  // writing references only
-      k2[i] = ((uint32_t)(MAX_LEN - min(len, MAX_LEN)) << 12) | (uint32_t)n;
+      k2[i] = ((uint32_t)(MAX_LEN - min(len, MAX_LEN)) << 13) | (uint32_t)n;
       atomicAdd(&s_hist[min(len, MAX_LEN + 1)], 1);
       atomicMax(&s_maxlen, len);
     }
@@ -263,13 +311,13 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
     }
     return;
   }
-  SortKeys(tmp.keys).Sort(k2, 0, 21);
+  SortKeys(tmp.keys).Sort(k2, 0, 22);
   __syncthreads();  // tmp is re-used as newrank[]
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
-    const int j = threadIdx.x * SORT_ITEMS + i;
-    if (k2[i] != INVALID) s_newrank[k2[i] & 0xFFFu] = (uint16_t)j;
+    const int j = threadIdx.x * ITEMS + i;
+    if (k2[i] != INVALID) s_newrank[k2[i] & 0x1FFFu] = (uint16_t)j;
   }
   // jd[k] = sum_{j<k} count_j, count_j = #nodes with len > j
   if (threadIdx.x == 0)
@@ -298,44 +346,44 @@ k_chunk_build(const uint32_t *e2n, const uint32_t *pnode, const uint32_t *mv_xyz
   __syncthreads();
   const uint64_t noff = node_off[c];
   for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS) jd_out[c * (uint64_t)jdStride + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
+  // absent node: read the chunk's zero entry un[nloc], write to the trash position behind the diagonals
+  const uint32_t trash = (uint32_t)s_jd[MAX_LEN + 1];
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++)
+  for (int i = 0; i < ITEMS; i++)
   {
-    const int posn = threadIdx.x * SORT_ITEMS + i;
-    // rank-major inside the chunk; with the XOR schedule slot s of an element with Morton child
-    // number c holds lattice rank s ^ c (both rows), so that siblings touch the SAME node in the
-    // same instruction (shared-memory broadcast) - see k_mv3
-    int q = val[i] % spe;
-    const int el = val[i] / spe;
-    if (xorperm && val[i] < nslots)
+    const int sv = val[i] & 0x1FFF;
+    if (sv >= nslots) continue;  // padding item of the sort
+    // slot-major inside the chunk: a warp (consecutive units) reads consecutive words
+    const int q = sv % spu;
+    const int el = sv / spu;
+    uint32_t nr = (uint32_t)nloc, pos = trash;
+    if (key[i] != INVALID)
     {
-      const uint64_t ge = elem0 + e0 + el;
-      const int L = mv_lev[ge];
-      int cnum = 0;
-      for (int d = 0; d < dim; d++) cnum |= ((mv_xyz[ge * dim + d] >> (max_depth - L)) & 1u) << d;
-      q = (q < N) ? (q ^ cnum) : (N + ((q - N) ^ cnum));
+      const int n0 = rank0[i];
+      const int k = (int)cwi[i] - (int)s_cw[n0];
+      nr = s_newrank[n0];
+      if (wr[i]) pos = (uint32_t)s_jd[k] + nr;
     }
-    const uint64_t dst = e0 * spe + (uint64_t)q * elemsPerChunk + el;
-    // absent node: read the chunk's zero entry un[nloc], write to the trash position behind the diagonals
-    const uint32_t trash = (uint32_t)s_jd[MAX_LEN + 1];
-    if (key[i] == INVALID)
+    if (!split16) slot[u0 * spu + (uint64_t)q * upc + el] = nr | (pos << 16);
+    else
     {
-      if (val[i] < nslots) slot[dst] = (uint32_t)nloc | (trash << 16);
-      continue;
+      const uint64_t w16 = (u0 * (uint64_t)(spu / 2) + (uint64_t)(q >> 1) * upc + el) * 2 + (q & 1);
+      rk16[w16] = (uint16_t)nr;
+      ps16[w16] = (uint16_t)pos;
     }
-    const int n0 = rank0[i];
-    const int k = (int)cwi[i] - (int)s_cw[n0];
-    const int nr = s_newrank[n0];
-    slot[dst] = (uint32_t)nr | ((wr[i] ? (uint32_t)(s_jd[k] + nr) : trash) << 16);
-    (void)posn;
-    if (head[i])
+    if (key[i] != INVALID && head[i])
     {
+      const int n0 = rank0[i];
       const int len = (int)s_cw[n0 + 1] - (int)s_cw[n0];
       uint32_t m = (uint32_t)len | META_PRESENT;
       if (refcnt[key[i]] != (uint32_t)len) m |= META_SHARED;
       if (isbdy[key[i]]) m |= META_BDY;
-      gid_out[noff + nr] = key[i];
-      meta_out[noff + nr] = (uint16_t)m;
+      if (!split16)
+      {
+        gid_out[noff + nr] = key[i];
+        meta_out[noff + nr] = (uint16_t)m;
+      }
+      else rec_out[noff + nr] = make_uint2(key[i], m);
     }
   }
 }
@@ -349,37 +397,34 @@ __global__ void k_max_u32(const uint32_t *in, uint64_t n, uint32_t *out)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   uint32_t v = i < n ? in[i] : 0;
+#ifndef DKT_EMU
   for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+#else
+  atomicMax(out, v);
+#endif
 }
 
-static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t hang0, uint64_t nSet, int rows, int phase, const uint32_t *refcnt)
+// Chunk tables of one set from its unit slot table U (freed by the caller).
+static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *refcnt)
 {
-  cs = ChunkSet();
-  cs.rows = rows;
-  cs.phase = phase;
-  cs.elem0 = elem0;
-  cs.hang0 = hang0;
-  cs.nElem = nSet;
+  const uint64_t nSet = cs.nElem;
   if (nSet == 0) return DKT_OK;
-  const int N = da.N;
-  cs.elemsPerChunk = rows_per_chunk(N) / rows;
-  cs.nChunks = (uint32_t)((nSet + cs.elemsPerChunk - 1) / cs.elemsPerChunk);
+  const int spu = cs.spu, upc = (int)cs.elemsPerChunk, split16 = cs.kind == 1 ? 1 : 0;
+  cs.nChunks = (uint32_t)((nSet + upc - 1) / upc);
   uint32_t *nloc = nullptr, *mlen = nullptr;
   uint64_t *wide = nullptr, *off = nullptr;
   CK(cudaMalloc((void **)&nloc, (size_t)cs.nChunks * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&mlen, (size_t)cs.nChunks * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&wide, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
   CK(cudaMalloc((void **)&off, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
-  const int xorperm = da.order == 1 ? 1 : 0;
-  cs.xorperm = xorperm;
-  k_chunk_build<false><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode + hang0 * N, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
-                                                                    xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
-                                                                    da.d_node_isbdy, nullptr, 0, nloc, mlen, nullptr, nullptr, nullptr,
-                                                                    nullptr);
+  auto kcount = split16 ? k_chunk_build<false, SORT_ITEMS_GRP> : k_chunk_build<false, SORT_ITEMS>;
+  auto kwrite = split16 ? k_chunk_build<true, SORT_ITEMS_GRP> : k_chunk_build<true, SORT_ITEMS>;
+  DKT_LAUNCH(kcount, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, split16, refcnt, da.d_node_isbdy, nullptr, 0, nloc, mlen,
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
   CK(cudaMemsetAsync(wide, 0, ((size_t)cs.nChunks + 1) * sizeof(uint64_t), da.stream));
-  k_u32_widen<<<(cs.nChunks + 255) / 256, 256, 0, da.stream>>>(nloc, cs.nChunks, wide);
+  DKT_LAUNCH(k_u32_widen, nblk(cs.nChunks), 256, 0, da.stream)(nloc, cs.nChunks, wide);
   g_launches++;
   int rc = device_exclusive_scan(da, wide, off, (uint64_t)cs.nChunks + 1);
   if (rc) return rc;
@@ -388,8 +433,8 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t hang0, uint6
   uint32_t *dmax = nullptr, hmax[2] = {0, 0};
   CK(cudaMalloc((void **)&dmax, 2 * sizeof(uint32_t)));
   CK(cudaMemsetAsync(dmax, 0, 2 * sizeof(uint32_t), da.stream));
-  k_max_u32<<<(cs.nChunks + 255) / 256, 256, 0, da.stream>>>(nloc, cs.nChunks, dmax);
-  k_max_u32<<<(cs.nChunks + 255) / 256, 256, 0, da.stream>>>(mlen, cs.nChunks, dmax + 1);
+  DKT_LAUNCH(k_max_u32, nblk(cs.nChunks), 256, 0, da.stream)(nloc, cs.nChunks, dmax);
+  DKT_LAUNCH(k_max_u32, nblk(cs.nChunks), 256, 0, da.stream)(mlen, cs.nChunks, dmax + 1);
   g_launches += 2;
   CK(cudaMemcpyAsync(hmax, dmax, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, da.stream));
   CK(cudaStreamSynchronize(da.stream));
@@ -399,14 +444,23 @@ static int build_set(DA &da, ChunkSet &cs, uint64_t elem0, uint64_t hang0, uint6
   cs.jdStride = (cs.maxLen + 1 + 7) & ~7u;
   cs.totalNodes = total;
   cs.d_node_off = off;
-  CK(cudaMalloc((void **)&cs.d_slot, (size_t)cs.nChunks * cs.elemsPerChunk * rows * N * sizeof(uint32_t)));
-  CK(cudaMalloc((void **)&cs.d_gid, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
-  CK(cudaMalloc((void **)&cs.d_meta, std::max<uint64_t>(total, 1) * sizeof(uint16_t)));
+  const size_t nslotsAll = (size_t)cs.nChunks * upc * spu;
+  if (!split16)
+  {
+    CK(cudaMalloc((void **)&cs.d_slot, nslotsAll * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&cs.d_gid, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&cs.d_meta, std::max<uint64_t>(total, 1) * sizeof(uint16_t)));
+  }
+  else
+  {
+    CK(cudaMalloc((void **)&cs.d_rk16, nslotsAll * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&cs.d_ps16, nslotsAll * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 1) * sizeof(uint2)));
+  }
   CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * sizeof(uint16_t)));
-  k_chunk_build<true><<<cs.nChunks, SORT_THREADS, 0, da.stream>>>(da.d_e2n, da.d_pnode + hang0 * N, da.d_mv_xyz, da.d_mv_lev, da.dim, da.max_depth,
-                                                                   xorperm, elem0, nSet, N, rows, cs.elemsPerChunk, refcnt,
-                                                                   da.d_node_isbdy, off, (int)cs.jdStride, nullptr, nullptr, cs.d_slot,
-                                                                   cs.d_gid, cs.d_meta, cs.d_jd);
+  DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, split16, refcnt, da.d_node_isbdy, off, (int)cs.jdStride, nullptr,
+                                                              nullptr, cs.d_slot, cs.d_rk16, cs.d_ps16, cs.d_gid, cs.d_meta, (uint2 *)cs.d_rec,
+                                                              cs.d_jd);
   g_launches++;
   CK(cudaStreamSynchronize(da.stream));
   CK(cudaGetLastError());
@@ -426,6 +480,8 @@ void free_chunks(DA &da)
   for (ChunkSet &cs : da.sets)
   {
     cudaFree(cs.d_slot); cudaFree(cs.d_gid); cudaFree(cs.d_meta); cudaFree(cs.d_jd); cudaFree(cs.d_node_off);
+    cudaFree(cs.d_rk16); cudaFree(cs.d_ps16); cudaFree(cs.d_rec);
+    for (void *p : cs.owned) cudaFree(p);
   }
   da.sets.clear();
 }
@@ -440,53 +496,380 @@ __global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_
   child[i] = (uint8_t)(L ? c : 0);
 }
 
+// ---- sibling groups: discovery ---------------------------------------------------------------
+// d_mv_src is the position of every visited element in the visit (SFC) order; a complete family of leaves
+// is 2^dim consecutive positions with one parent.
+__global__ void k_invert_src(const uint32_t *src, uint64_t n, uint32_t *inv)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) inv[src[i]] = (uint32_t)i;
+}
+__global__ void k_family_heads(const uint32_t *inv, const uint32_t *xyz, const uint8_t *lev, uint64_t n, int dim, int max_depth,
+                               uint64_t *head)
+{
+  uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j > n) return;
+  if (j == n) { head[j] = 0; return; }
+  const int nch = 1 << dim;
+  uint64_t h = 0;
+  if (j + nch <= n)
+  {
+    const uint32_t a = inv[j];
+    const int L = lev[a];
+    if (L >= 1)
+    {
+      const uint32_t pmask = ~((2u << (max_depth - L)) - 1u);
+      uint32_t seen = 0;
+      bool ok = true;
+      for (int t = 0; t < nch && ok; t++)
+      {
+        const uint32_t b = inv[j + t];
+        if (lev[b] != L) { ok = false; break; }
+        int c = 0;
+        for (int d = 0; d < dim; d++)
+        {
+          const uint32_t x = xyz[(uint64_t)b * dim + d];
+          if ((x & pmask) != (xyz[(uint64_t)a * dim + d] & pmask)) ok = false;
+          c |= ((x >> (max_depth - L)) & 1u) << d;
+        }
+        seen |= 1u << c;
+      }
+      h = (ok && seen == (nch == 32 ? 0xFFFFFFFFu : ((1u << nch) - 1u))) ? 1 : 0;
+    }
+  }
+  head[j] = h;
+}
+// mem[f * 2^dim + c] = visited-element index of child c of family f; infam[e] = 1
+__global__ void k_family_members(const uint32_t *inv, const uint64_t *head, const uint64_t *fpos, const uint8_t *child, uint64_t n, int dim,
+                                 uint32_t *mem, uint8_t *infam)
+{
+  uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j >= n || !head[j]) return;
+  const int nch = 1 << dim;
+  const uint64_t f = fpos[j];
+  for (int t = 0; t < nch; t++)
+  {
+    const uint32_t b = inv[j + t];
+    mem[f * nch + child[b]] = b;
+    infam[b] = 1;
+  }
+}
+// group (f, cR) is hanging if one of its 2^g members is
+__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, uint64_t nReg, uint64_t *ghang)
+{
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u > nGroups) return;
+  if (u == nGroups) { ghang[u] = 0; return; }
+  const int NR = 1 << (dim - g), NC = 1 << g;
+  const uint64_t f = u / NR;
+  const int cR = (int)(u % NR);
+  uint64_t h = 0;
+  for (int cG = 0; cG < NC; cG++)
+    if (mem[(f << dim) + ((cR << g) | cG)] >= nReg) h = 1;
+  ghang[u] = h;
+}
+// member lists of the regular / hanging groups, both in (family, cR) order
+__global__ void k_group_lists(const uint32_t *mem, const uint64_t *ghang, const uint64_t *hpos, uint64_t nGroups, int dim, int g,
+                              uint32_t *listR, uint32_t *listH)
+{
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= nGroups) return;
+  const int NR = 1 << (dim - g), NC = 1 << g;
+  const uint64_t f = u / NR;
+  const int cR = (int)(u % NR);
+  uint32_t *dst = ghang[u] ? listH + hpos[u] * NC : listR + (u - hpos[u]) * NC;
+  for (int cG = 0; cG < NC; cG++) dst[cG] = mem[(f << dim) + ((cR << g) | cG)];
+}
+__global__ void k_single_flags(const uint8_t *infam, uint64_t n, uint64_t lo, uint64_t hi, uint64_t *flag)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  flag[i] = (i < n && i >= lo && i < hi && !infam[i]) ? 1 : 0;
+}
+__global__ void k_compact(const uint64_t *flag, const uint64_t *pos, uint64_t n, uint32_t *list)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) list[pos[i]] = (uint32_t)i;
+}
+// compact copies of the per-element arrays of the elements in `list`
+__global__ void k_gather_single(const uint32_t *list, uint64_t n, int N, uint64_t nReg, const uint32_t *e2n, const uint32_t *pnode,
+                                const uint8_t *lev, const uint8_t *child, uint32_t *e2n_s, uint32_t *pnode_s, uint8_t *lev_s,
+                                uint8_t *child_s)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t e = list[i];
+  for (int r = 0; r < N; r++) e2n_s[i * N + r] = e2n[(uint64_t)e * N + r];
+  if (pnode_s)
+    for (int r = 0; r < N; r++) pnode_s[i * N + r] = pnode[((uint64_t)e - nReg) * N + r];
+  lev_s[i] = lev[e];
+  child_s[i] = child[e];
+}
+// Unit slot table of a group set.  Own slot l = xg + 3^g * sR: xg = sum_{d<g} x_d 3^d is the position in the
+// family's 3-point lattice of the grouped dimensions, sR the XOR-permuted rank bits of the others (lattice
+// bit s_d ^ c_d, the group's members share c_d for d >= g).  Slots LP.. (hanging groups): parent-lattice
+// rank (qG natural, tR ^ cR).  The table is padded to an even number of slots per unit.
+__global__ void k_unit_slots_group(const uint32_t *list, uint64_t nUnits, int dim, int g, int hang, uint64_t nReg, const uint32_t *e2n,
+                                   const uint32_t *pnode, const uint8_t *child, const uint8_t *lev, uint32_t *U, uint8_t *lev_g,
+                                   unsigned long long *fmask64)
+{
+  const int N = 1 << dim, NC = 1 << g, NR = 1 << (dim - g);
+  int L3 = 1;
+  for (int d = 0; d < g; d++) L3 *= 3;
+  const int LP = L3 * NR, spu = (LP + (hang ? N : 0) + 1) & ~1;
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nUnits * spu) return;
+  const uint64_t u = i / spu;
+  const int q = (int)(i % spu);
+  const uint32_t *m = list + u * NC;
+  const int cR = child[m[0]] >> g;
+  uint32_t key = INVALID;
+  if (q < LP)
+  {
+    const int xg = q % L3, sR = q / L3;
+    for (int cG = 0; cG < NC; cG++)
+    {
+      int rG = 0, rem = xg;
+      bool ok = true;
+      for (int d = 0; d < g; d++)
+      {
+        const int r = (rem % 3) - ((cG >> d) & 1);
+        rem /= 3;
+        if (r < 0 || r > 1) ok = false;
+        else rG |= r << d;
+      }
+      if (!ok) continue;
+      const uint32_t k = e2n[(uint64_t)m[cG] * N + (rG | ((sR ^ cR) << g))];
+      if (k != INVALID) key = k;
+    }
+  }
+  else if (q < LP + (hang ? N : 0))
+  {
+    const int t = q - LP;
+    const int pr = (t & (NC - 1)) | (((t >> g) ^ cR) << g);
+    for (int cG = 0; cG < NC; cG++)
+      if (m[cG] >= nReg) { key = pnode[((uint64_t)m[cG] - nReg) * N + pr]; break; }
+  }
+  U[i] = key;
+  if (q == 0) lev_g[u] = lev[m[0]];
+  if (hang && q < LP && key != INVALID) atomicOr(fmask64 + u, 1ull << q);
+}
+
+static int scan_total(DA &da, const uint64_t *flag, uint64_t *pos, uint64_t n, uint64_t &total)
+{
+  int rc = device_exclusive_scan(da, flag, pos, n + 1);
+  if (rc) return rc;
+  CK(cudaMemcpy(&total, pos + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DKT_OK;
+}
+
+struct PendingSet
+{
+  size_t idx;       // index into da.sets
+  uint32_t *U;      // unit slot table (temporary)
+};
+
+// per-element set over contiguous per-element arrays (the DA's own, or compact copies of the ungrouped elements)
+static int add_elem_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *e2n, const uint32_t *pnode, const uint8_t *lev,
+                        const uint8_t *child, const uint32_t *fmask, uint64_t n, int rows, int phase, uint64_t elem0, uint64_t hang0)
+{
+  if (n == 0) return DKT_OK;
+  da.sets.emplace_back();
+  ChunkSet &cs = da.sets.back();
+  cs.rows = rows; cs.phase = phase; cs.elem0 = elem0; cs.hang0 = hang0; cs.nElem = n; cs.kind = 0;
+  cs.xorperm = da.order == 1 ? 1 : 0;
+  cs.spu = rows * da.N;
+  cs.elemsPerChunk = rows_per_chunk(da.N) / rows;
+  cs.lev = lev; cs.child = child; cs.fmask = fmask;
+  uint32_t *U = nullptr;
+  CK(cudaMalloc((void **)&U, n * cs.spu * sizeof(uint32_t)));
+  DKT_LAUNCH(k_unit_slots_elem, nblk(n * cs.spu), 256, 0, da.stream)(e2n, pnode, child, n, da.N, rows, cs.xorperm, U);
+  g_launches++;
+  pend.push_back({da.sets.size() - 1, U});
+  return DKT_OK;
+}
+
+static int add_group_set(DA &da, std::vector<PendingSet> &pend, uint32_t *list, uint64_t n, int g, int hang)
+{
+  if (n == 0) { cudaFree(list); return DKT_OK; }
+  da.sets.emplace_back();
+  ChunkSet &cs = da.sets.back();
+  int L3 = 1;
+  for (int d = 0; d < g; d++) L3 *= 3;
+  const int LP = L3 << (da.dim - g);
+  cs.rows = hang ? 2 : 1; cs.phase = 0; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
+  cs.spu = (LP + (hang ? da.N : 0) + 1) & ~1;
+  cs.elemsPerChunk = std::min(SLOT_CAP_GRP / cs.spu, GRP_TPB);
+  uint32_t *U = nullptr;
+  uint8_t *lev_g = nullptr;
+  unsigned long long *fm = nullptr;
+  CK(cudaMalloc((void **)&U, n * cs.spu * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&lev_g, n));
+  CK(cudaMalloc((void **)&fm, n * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(fm, 0, n * sizeof(unsigned long long), da.stream));
+  DKT_LAUNCH(k_unit_slots_group, nblk(n * cs.spu), 256, 0, da.stream)(list, n, da.dim, g, hang, da.nReg, da.d_e2n, da.d_pnode, da.d_mv_child,
+                                                                        da.d_mv_lev, U, lev_g, fm);
+  g_launches++;
+  cs.lev = lev_g; cs.fmask64 = (const uint64_t *)fm;
+  cs.owned.push_back(lev_g); cs.owned.push_back(fm); cs.owned.push_back(list);
+  pend.push_back({da.sets.size() - 1, U});
+  return DKT_OK;
+}
+
+// DKT_GROUPS=g: group the leaves of complete sibling families (see the file header).  0 / unset: off.
+static int groups_requested(const DA &da)
+{
+  const char *e = getenv("DKT_GROUPS");
+  if (!e) return 0;
+  const int g = atoi(e);
+  if (g <= 0 || da.order != 1 || da.phased || g > da.dim) return 0;
+  if (!((da.dim == 4 && (g == 2 || g == 3)) || (da.dim == 3 && g == 3) || (da.dim == 2 && g == 2))) return 0;
+  return g;
+}
+
 int build_chunks(DA &da)
 {
+  if (da.nNodes >= 0x7FFFFFFFull) { set_error("more than 2^31 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
   CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
-  k_child_numbers<<<(unsigned)((da.nMv + 255) / 256), 256, 0, da.stream>>>(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth,
-                                                                           da.d_mv_child);
+  DKT_LAUNCH(k_child_numbers, nblk(da.nMv), 256, 0, da.stream)(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth, da.d_mv_child);
   g_launches++;
-  uint32_t *refcnt = nullptr;
-  CK(cudaMalloc((void **)&refcnt, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t)));
-  CK(cudaMemsetAsync(refcnt, 0, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t), da.stream));
-  const uint64_t n1 = da.nMv * (uint64_t)da.N, n2 = da.nHang * (uint64_t)da.N;
-  if (n1) { k_ref_count<<<(unsigned)((n1 + 255) / 256), 256, 0, da.stream>>>(da.d_e2n, nullptr, n1, refcnt); g_launches++; }
-  if (n2)
+  const int N = da.N;
+  const int xorperm = da.order == 1 ? 1 : 0;
+  if (da.nHang)
   {
-    k_ref_count<<<(unsigned)((n2 + 255) / 256), 256, 0, da.stream>>>(da.d_pnode, da.d_e2n + da.nReg * (uint64_t)da.N, n2, refcnt);
     CK(cudaMalloc((void **)&da.d_fmask, da.nHang * sizeof(uint32_t)));
-    k_fmask<<<(unsigned)((da.nHang + 255) / 256), 256, 0, da.stream>>>(da.d_e2n + da.nReg * (uint64_t)da.N, da.d_mv_child + da.nReg, da.nHang,
-                                                                       da.N, da.order == 1 ? 1 : 0, da.d_fmask);
-    g_launches += 2;
+    DKT_LAUNCH(k_fmask, nblk(da.nHang), 256, 0, da.stream)(da.d_e2n + da.nReg * (uint64_t)N, da.d_mv_child + da.nReg, da.nHang, N, xorperm,
+                                                           da.d_fmask);
+    g_launches++;
   }
-  // element ranges: one regular + one hanging set, or (partitioned) three phases of each:
-  // interior first half / boundary / interior second half - see run_matvec_dist
-  struct Range { uint64_t a, b; int phase; };
-  std::vector<Range> rr, hr;
-  if (da.phased)
+  std::vector<PendingSet> pend;
+  int rc = DKT_OK;
+  const int g = groups_requested(da);
+  da.groups = g;
+  if (!g)
   {
-    const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
-    rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
-    hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
+    // element ranges: one regular + one hanging set, or (partitioned) three phases of each:
+    // interior first half / boundary / interior second half - see run_matvec_dist
+    struct Range { uint64_t a, b; int phase; };
+    std::vector<Range> rr, hr;
+    if (da.phased)
+    {
+      const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
+      rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
+      hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
+    }
+    else
+    {
+      rr = {{0, da.nReg, 0}};
+      hr = {{0, da.nHang, 0}};
+    }
+    for (const Range &r : rr)
+      if (rc == DKT_OK && r.b > r.a)
+        rc = add_elem_set(da, pend, da.d_e2n + r.a * N, nullptr, da.d_mv_lev + r.a, da.d_mv_child + r.a, nullptr, r.b - r.a, 1, r.phase, r.a, 0);
+    for (const Range &r : hr)
+      if (rc == DKT_OK && r.b > r.a)
+        rc = add_elem_set(da, pend, da.d_e2n + (da.nReg + r.a) * N, da.d_pnode + r.a * N, da.d_mv_lev + da.nReg + r.a,
+                          da.d_mv_child + da.nReg + r.a, da.d_fmask + r.a, r.b - r.a, 2, r.phase, da.nReg + r.a, r.a);
   }
   else
   {
-    rr = {{0, da.nReg, 0}};
-    hr = {{0, da.nHang, 0}};
+    const uint64_t n = da.nMv;
+    const int nch = 1 << da.dim, NC = 1 << g, NR = 1 << (da.dim - g);
+    uint32_t *inv = nullptr, *mem = nullptr;
+    uint64_t *flag = nullptr, *pos = nullptr;
+    uint8_t *infam = nullptr;
+    CK(cudaMalloc((void **)&inv, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&flag, (n + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&pos, (n + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&infam, std::max<uint64_t>(n, 1)));
+    CK(cudaMemsetAsync(infam, 0, std::max<uint64_t>(n, 1), da.stream));
+    DKT_LAUNCH(k_invert_src, nblk(n), 256, 0, da.stream)(da.d_mv_src, n, inv);
+    DKT_LAUNCH(k_family_heads, nblk(n + 1), 256, 0, da.stream)(inv, da.d_mv_xyz, da.d_mv_lev, n, da.dim, da.max_depth, flag);
+    g_launches += 2;
+    uint64_t nFam = 0;
+    rc = scan_total(da, flag, pos, n, nFam);
+    if (rc) return rc;
+    CK(cudaMalloc((void **)&mem, std::max<uint64_t>(nFam, 1) * nch * sizeof(uint32_t)));
+    DKT_LAUNCH(k_family_members, nblk(n), 256, 0, da.stream)(inv, flag, pos, da.d_mv_child, n, da.dim, mem, infam);
+    g_launches++;
+    // groups -> regular / hanging lists
+    const uint64_t nGroups = nFam * NR;
+    uint64_t *gh = nullptr, *gpos = nullptr;
+    CK(cudaMalloc((void **)&gh, (nGroups + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&gpos, (nGroups + 1) * sizeof(uint64_t)));
+    DKT_LAUNCH(k_group_class, nblk(nGroups + 1), 256, 0, da.stream)(mem, nGroups, da.dim, g, da.nReg, gh);
+    g_launches++;
+    uint64_t nGH = 0;
+    rc = scan_total(da, gh, gpos, nGroups, nGH);
+    if (rc) return rc;
+    const uint64_t nGR = nGroups - nGH;
+    uint32_t *listR = nullptr, *listH = nullptr;
+    CK(cudaMalloc((void **)&listR, std::max<uint64_t>(nGR, 1) * NC * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&listH, std::max<uint64_t>(nGH, 1) * NC * sizeof(uint32_t)));
+    if (nGroups)
+    {
+      DKT_LAUNCH(k_group_lists, nblk(nGroups), 256, 0, da.stream)(mem, gh, gpos, nGroups, da.dim, g, listR, listH);
+      g_launches++;
+    }
+    rc = add_group_set(da, pend, listR, nGR, g, 0);
+    if (rc == DKT_OK) rc = add_group_set(da, pend, listH, nGH, g, 1);
+    // the elements outside complete families: compact copies, per-element sets
+    for (int hang = 0; hang < 2 && rc == DKT_OK; hang++)
+    {
+      const uint64_t lo = hang ? da.nReg : 0, hi = hang ? n : da.nReg;
+      DKT_LAUNCH(k_single_flags, nblk(n + 1), 256, 0, da.stream)(infam, n, lo, hi, flag);
+      g_launches++;
+      uint64_t nS = 0;
+      rc = scan_total(da, flag, pos, n, nS);
+      if (rc || !nS) continue;
+      uint32_t *list = nullptr, *e2n_s = nullptr, *pnode_s = nullptr, *fm_s = nullptr;
+      uint8_t *lev_s = nullptr, *child_s = nullptr;
+      CK(cudaMalloc((void **)&list, nS * sizeof(uint32_t)));
+      CK(cudaMalloc((void **)&e2n_s, nS * N * sizeof(uint32_t)));
+      if (hang) CK(cudaMalloc((void **)&pnode_s, nS * N * sizeof(uint32_t)));
+      if (hang) CK(cudaMalloc((void **)&fm_s, nS * sizeof(uint32_t)));
+      CK(cudaMalloc((void **)&lev_s, nS));
+      CK(cudaMalloc((void **)&child_s, nS));
+      DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
+      DKT_LAUNCH(k_gather_single, nblk(nS), 256, 0, da.stream)(list, nS, N, da.nReg, da.d_e2n, da.d_pnode, da.d_mv_lev, da.d_mv_child, e2n_s,
+                                                               pnode_s, lev_s, child_s);
+      g_launches += 2;
+      if (hang)
+      {
+        DKT_LAUNCH(k_fmask, nblk(nS), 256, 0, da.stream)(e2n_s, child_s, nS, N, xorperm, fm_s);
+        g_launches++;
+      }
+      rc = add_elem_set(da, pend, e2n_s, pnode_s, lev_s, child_s, fm_s, nS, hang ? 2 : 1, 0, 0, 0);
+      if (rc == DKT_OK)
+      {
+        ChunkSet &cs = da.sets.back();
+        cs.owned.push_back(lev_s); cs.owned.push_back(child_s);
+        if (fm_s) cs.owned.push_back(fm_s);
+      }
+      CK(cudaStreamSynchronize(da.stream));
+      cudaFree(list); cudaFree(e2n_s); cudaFree(pnode_s);
+    }
+    CK(cudaStreamSynchronize(da.stream));
+    cudaFree(inv); cudaFree(mem); cudaFree(flag); cudaFree(pos); cudaFree(infam); cudaFree(gh); cudaFree(gpos);
   }
-  int rc = DKT_OK;
-  for (const Range &r : rr)
+  // writing references of every node over all sets, then the chunk tables
+  uint32_t *refcnt = nullptr;
+  CK(cudaMalloc((void **)&refcnt, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(refcnt, 0, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t), da.stream));
+  for (const PendingSet &ps : pend)
   {
-    if (rc != DKT_OK || r.b <= r.a) continue;
-    da.sets.emplace_back();
-    rc = build_set(da, da.sets.back(), r.a, 0, r.b - r.a, 1, r.phase, refcnt);
+    const ChunkSet &cs = da.sets[ps.idx];
+    const uint64_t ns = cs.nElem * cs.spu;
+    if (rc == DKT_OK && ns)
+    {
+      DKT_LAUNCH(k_ref_count, nblk(ns), 256, 0, da.stream)(ps.U, ns, refcnt);
+      g_launches++;
+    }
   }
-  for (const Range &r : hr)
-  {
-    if (rc != DKT_OK || r.b <= r.a) continue;
-    da.sets.emplace_back();
-    rc = build_set(da, da.sets.back(), da.nReg + r.a, r.a, r.b - r.a, 2, r.phase, refcnt);
-  }
+  for (const PendingSet &ps : pend)
+    if (rc == DKT_OK) rc = build_set(da, da.sets[ps.idx], ps.U, refcnt);
+  cudaStreamSynchronize(da.stream);
+  for (const PendingSet &ps : pend) cudaFree(ps.U);
   cudaFree(refcnt);
   int dev = 0;
   CK(cudaGetDevice(&dev));
@@ -512,6 +895,9 @@ struct Mv3Params
   const uint8_t *lev;    // level of the set's elements
   const uint8_t *child;  // Morton child numbers of the set's elements
   const uint32_t *fmask; // hanging set: filled own slots (slot order)
+  const uint32_t *rk16, *ps16;   // group sets: 16-bit node ranks / positions, two slots per word
+  const uint2 *rec;              // group sets: {gid, meta} per chunk node
+  const uint64_t *fmask64;       // hanging group sets: filled own lattice slots
   uint32_t nSet, nChunks, elemsPerChunk, xcap, ncap, jdStride;
   int q1mask;
   int exact_ip;          // order 1: ip0/ip1 equal the exact interpolation to 1e-13
@@ -662,13 +1048,19 @@ __device__ __forceinline__ void apply_op3(const Mv3Params<DIM, ORDER> &p, int le
   }
 }
 
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+#ifndef DKT_EMU
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#else
+inline void cp_async8(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 8); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#endif
 
 // undo the XOR slot schedule in registers: v[r] <- v[r ^ c]
 template <int DIM, int N, typename T>
@@ -700,7 +1092,7 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int M = ORDER + 1;
   constexpr int ROWS = HANG ? 2 : 1;
-  extern __shared__ double sm[];
+  DKT_DYN_SMEM(double, sm);
   double *X = sm;                                   // [xcap]
   double *unb = sm + p.xcap;                        // [2][ncap]
   int *jdb = (int *)(sm + p.xcap + 2 * p.ncap);     // [2][jdStride]
@@ -908,11 +1300,11 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
 }
 
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
-static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, const uint8_t *lev, const uint8_t *child)
+static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   p.slot = cs.d_slot; p.gid = cs.d_gid; p.meta = cs.d_meta; p.jd = cs.d_jd; p.node_off = cs.d_node_off;
-  p.lev = lev; p.child = child; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
+  p.lev = cs.lev; p.child = cs.child; p.fmask = cs.fmask; p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
   p.xcap = (uint32_t)rows_per_chunk(N) * N + 258u;  // + padding of the first 16 diagonals + the trash position
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
@@ -928,9 +1320,376 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p, cons
   int sms = da.numSMs;
   if (da.phased && cs.phase != 1) sms = std::max(1, da.numSMs - da.commSMs);
   const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * sms));
-  kern<<<grid, TPB, smem, da.stream>>>(p);
+  DKT_LAUNCH(kern, grid, TPB, smem, da.stream)(p);
   g_launches++;
   return DKT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sibling-group kernel (order 1, identity / Walsh-Hadamard operators, exact interpolation)
+// ------------------------------------------------------------------------------------------
+// One thread per GROUP: the 2^G leaves of a complete sibling family that share the child-number bits of the
+// dimensions >= G.  Their nodes form a 3^G x 2^(DIM-G) lattice (LP slots; the dimensions >= G keep the XOR
+// schedule, so the 2^(DIM-G) groups of a family still read the same node in the same instruction).  Per group:
+// LP gathers, 2^G elemental operators on register-resident values with STATIC indices, LP scatters; a hanging
+// group additionally reads the 2^DIM parent nodes once, interpolates them to the whole lattice (exact order-1
+// interpolation: midpoints) and scatters one masked transposed sum.  Quirk Q1 (FEM/include/matvec.h:517) is
+// applied per child at run time from the 64-bit fill mask, so every parent slot is a writing slot here.
+// Pipeline per chunk (two barriers): node records {gid, meta} are staged in shared memory by cp.async - every
+// thread copies, consumes and later overwrites only its OWN records -, the gather of chunk i+1 is issued right
+// after barrier A and stays in flight during the whole of chunk i.
+template <int DIM, int G>
+struct Grp
+{
+  static constexpr int N = 1 << DIM, NC = 1 << G, NR = 1 << (DIM - G);
+  static constexpr int L3 = (G == 1 ? 3 : G == 2 ? 9 : G == 3 ? 27 : 81);
+  static constexpr int LP = L3 * NR;
+  // lattice slot of rank r (grouped bits natural, the others XOR-permuted) of child cG
+  __host__ __device__ static constexpr int lat(int cG, int r)
+  {
+    int xg = 0, p3 = 1;
+    for (int d = 0; d < G; d++)
+    {
+      xg += (((cG >> d) & 1) + ((r >> d) & 1)) * p3;
+      p3 *= 3;
+    }
+    return xg + L3 * (r >> G);
+  }
+  // child cG is the first (smallest) child touching the lattice point of its rank r
+  __host__ __device__ static constexpr bool first(int cG, int r) { return ((cG & ~r) & (NC - 1)) == 0; }
+};
+
+// parent values (index: grouped bits natural | other bits already interpolated) -> lattice, one grouped dimension
+// at a time: src index a + 3^K * b (b's lowest bit = parent corner along dimension K), dst index a + 3^K * x + 3^(K+1) * (b >> 1)
+template <int DIM, int G, int K>
+__device__ __forceinline__ void grp_expand(const double *src, double *dst)
+{
+  constexpr int P3 = (K == 0 ? 1 : K == 1 ? 3 : K == 2 ? 9 : 27);
+  constexpr int NB = 1 << (DIM - K - 1);
+#pragma unroll
+  for (int b = 0; b < NB; b++)
+#pragma unroll
+    for (int a = 0; a < P3; a++)
+    {
+      const double lo = src[a + P3 * (2 * b)], hi = src[a + P3 * (2 * b + 1)];
+      dst[a + 3 * P3 * b] = lo;
+      dst[a + P3 + 3 * P3 * b] = 0.5 * (lo + hi);
+      dst[a + 2 * P3 + 3 * P3 * b] = hi;
+    }
+}
+
+template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
+__global__ void __launch_bounds__(TPB, DKT_GRP_MINB) k_mvg(const __grid_constant__ Mv3Params<DIM, 1> p)
+{
+  using GP = Grp<DIM, G>;
+  constexpr int N = GP::N, LP = GP::LP, NC = GP::NC;
+  constexpr int SPU = (LP + (HANG ? N : 0) + 1) & ~1;
+  constexpr int NW = SPU / 2;
+  DKT_DYN_SMEM(double, sm);
+  double *X = sm;                                      // [xcap]
+  double *unb = sm + p.xcap;                           // [2][ncap]
+  uint2 *recb = (uint2 *)(sm + p.xcap + 2 * p.ncap);   // [2][ncap]
+  int *jdb = (int *)(recb + 2 * p.ncap);               // [2][jdStride]
+
+  const int tid = threadIdx.x;
+  const uint32_t E = p.elemsPerChunk;
+  uint64_t c = blockIdx.x;
+  if (c >= p.nChunks) return;
+
+  auto issue_rec = [&](uint64_t oa, int nloc, int b) {
+    uint2 *dst = recb + b * p.ncap;
+    for (int n = tid; n < nloc; n += TPB) cp_async8(dst + n, p.rec + oa + n);
+  };
+  auto issue_gather = [&](uint64_t cc, int nloc, int b) {
+    double *un = unb + b * p.ncap;
+    const uint2 *rec = recb + b * p.ncap;
+    if (tid == 0) un[nloc] = 0.0;  // the entry absent nodes read
+    for (int n = tid; n < nloc; n += TPB)
+    {
+      const uint2 r = rec[n];
+      if (DIRI && (r.y & META_BDY)) un[n] = 0.0;
+      else cp_async8(un + n, p.in + r.x);
+    }
+    int *jdn = jdb + b * p.jdStride;
+    for (int k = tid; k < (int)p.jdStride; k += TPB) jdn[k] = p.jd[cc * (uint64_t)p.jdStride + k];
+  };
+  uint32_t wr[NW];
+  int levU = 0;
+  uint64_t fm = 0;
+  auto load_ranks = [&](uint64_t cc) {
+    const uint64_t u0 = cc * (uint64_t)E;
+    const int nu = (int)min((uint64_t)E, (uint64_t)p.nSet - u0);
+    if (tid < nu)
+    {
+      const uint32_t *sw = p.rk16 + u0 * NW + tid;
+#pragma unroll
+      for (int j = 0; j < NW; j++) wr[j] = sw[(uint32_t)j * E];
+      levU = p.lev[u0 + tid];
+      if (HANG) fm = p.fmask64[u0 + tid];
+    }
+  };
+#define GRK(l) ((wr[(l) >> 1] >> (((l) & 1) * 16)) & 0xFFFFu)
+#define GPS(l) ((ps[(l) >> 1] >> (((l) & 1) * 16)) & 0xFFFFu)
+
+  // ---- prologue ---------------------------------------------------------------------------------
+  const uint64_t stride = gridDim.x;
+  uint64_t oa = p.node_off[c], ob = p.node_off[c + 1];
+  int nlocC = (int)(ob - oa);
+  issue_rec(oa, nlocC, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  issue_gather(c, nlocC, 0);
+  uint64_t cn = c + stride;
+  bool hasN = cn < p.nChunks;
+  int nlocN = 0;
+  if (hasN)
+  {
+    const uint64_t a = p.node_off[cn], b = p.node_off[cn + 1];
+    nlocN = (int)(b - a);
+    issue_rec(a, nlocN, 1);
+  }
+  cp_async_commit();
+  load_ranks(c);
+  int buf = 0;
+
+  while (true)
+  {
+    double *un = unb + buf * p.ncap;
+    const int *jd = jdb + buf * p.jdStride;
+    cp_async_wait_all();
+    __syncthreads();  // A: un/jd of this chunk visible, own records of the next chunk landed; X and un[buf^1] free
+    const uint64_t cnn = cn + stride;
+    const bool hasNN = hasN && cnn < p.nChunks;
+    uint64_t oaNN = 0;
+    int nlocNN = 0;
+    if (hasN)
+    {
+      issue_gather(cn, nlocN, buf ^ 1);
+      if (hasNN)
+      {
+        oaNN = p.node_off[cnn];
+        nlocNN = (int)(p.node_off[cnn + 1] - oaNN);
+      }
+    }
+    cp_async_commit();
+    // ---- T2: the groups of this chunk
+    {
+      const uint64_t u0 = c * (uint64_t)E;
+      const int nu = (int)min((uint64_t)E, (uint64_t)p.nSet - u0);
+      if (tid < nu)
+      {
+        uint32_t ps[NW];
+        {
+          const uint32_t *sw = p.ps16 + u0 * NW + tid;
+#pragma unroll
+          for (int j = 0; j < NW; j++) ps[j] = sw[(uint32_t)j * E];
+        }
+        const double s = p.lscale[levU];
+        double v[LP], o[LP];
+        if (!HANG)
+        {
+#pragma unroll
+          for (int l = 0; l < LP; l++) v[l] = un[GRK(l)];
+#pragma unroll
+          for (int cG = 0; cG < NC; cG++)
+          {
+            double e[N];
+#pragma unroll
+            for (int r = 0; r < N; r++) e[r] = v[GP::lat(cG, r)];
+            if (OPKIND == OP_HADAMARD)
+            {
+              wht<N>(e);
+#pragma unroll
+              for (int i = 0; i < N; i++) e[i] *= p.K[i] * s;
+              wht<N>(e);
+            }
+#pragma unroll
+            for (int r = 0; r < N; r++)
+            {
+              if (GP::first(cG, r)) o[GP::lat(cG, r)] = e[r];
+              else o[GP::lat(cG, r)] += e[r];
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < LP; l++) X[GPS(l)] = o[l];
+        }
+        else
+        {
+          {
+            // parent nodes -> whole lattice: subset sums along the XOR-permuted dimensions, midpoints along the grouped ones
+            double par[N];
+#pragma unroll
+            for (int t = 0; t < N; t++) par[t] = un[GRK(LP + t)];
+#pragma unroll
+            for (int b = NC; b < N; b <<= 1)
+#pragma unroll
+              for (int i = 0; i < N; i++)
+              {
+                if (i & b) continue;
+                par[i | b] = 0.5 * (par[i] + par[i | b]);
+              }
+            if constexpr (G == 1) grp_expand<DIM, G, 0>(par, v);
+            else if constexpr (G == 2)
+            {
+              double t1[3 * (N / 2)];
+              grp_expand<DIM, G, 0>(par, t1);
+              grp_expand<DIM, G, 1>(t1, v);
+            }
+            else
+            {
+              static_assert(G <= 3, "grouped dimensions");
+              double t1[3 * (N / 2)], t2[9 * (N / 4)];
+              grp_expand<DIM, G, 0>(par, t1);
+              grp_expand<DIM, G, 1>(t1, t2);
+              grp_expand<DIM, G, 2>(t2, v);
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < LP; l++)
+          {
+            const double own = un[GRK(l)];
+            if ((fm >> l) & 1ull) v[l] = own;
+          }
+          double ta[N];
+#pragma unroll
+          for (int cG = 0; cG < NC; cG++)
+          {
+            double e[N];
+#pragma unroll
+            for (int r = 0; r < N; r++) e[r] = v[GP::lat(cG, r)];
+            if (OPKIND == OP_HADAMARD)
+            {
+              wht<N>(e);
+#pragma unroll
+              for (int i = 0; i < N; i++) e[i] *= p.K[i] * s;
+              wht<N>(e);
+            }
+#pragma unroll
+            for (int r = 0; r < N; r++)
+            {
+              if (GP::first(cG, r)) o[GP::lat(cG, r)] = e[r];
+              else o[GP::lat(cG, r)] += e[r];
+              if ((fm >> GP::lat(cG, r)) & 1ull) e[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
+            }
+            // transposed interpolation of this child: A0^T along permuted dimensions and grouped ones with bit 0, A1^T otherwise
+#pragma unroll
+            for (int d = 0; d < DIM; d++)
+            {
+              const int b = 1 << d;
+              const bool a1 = (d < G) && ((cG >> d) & 1);
+#pragma unroll
+              for (int i = 0; i < N; i++)
+              {
+                if (i & b) continue;
+                if (!a1)
+                {
+                  const double h = 0.5 * e[i | b];
+                  e[i] += h;
+                  e[i | b] = h;
+                }
+                else
+                {
+                  const double h = 0.5 * e[i];
+                  e[i | b] += h;
+                  e[i] = h;
+                }
+              }
+            }
+            // quirk Q1: the LEAF's fill flag of rank q masks the contribution to the PARENT's rank q (matvec.h:517)
+#pragma unroll
+            for (int q = 0; q < N; q++)
+            {
+              const double t = ((fm >> GP::lat(cG, q)) & 1ull) ? 0.0 : e[q];
+              if (cG == 0) ta[q] = t;
+              else ta[q] += t;
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < LP; l++) X[GPS(l)] = o[l];
+#pragma unroll
+          for (int t = 0; t < N; t++) X[GPS(LP + t)] = ta[t];
+        }
+      }
+    }
+    if (hasN) load_ranks(cn);
+    __syncthreads();  // B: X complete
+    // ---- T4: own nodes of this chunk
+    {
+      const uint2 *rec = recb + buf * p.ncap;
+      for (int n = tid; n < nlocC; n += TPB)
+      {
+        const uint2 r = rec[n];
+        const int len = r.y & META_LEN;
+        if (len == 0) continue;  // only read by this chunk
+        double acc = X[n];       // jd[0] == 0
+        for (int j = 1; j < len; j++) acc += X[jd[j] + n];
+        if (DIRI && (r.y & META_BDY)) continue;
+        if (r.y & META_SHARED) atomicAdd(p.out + r.x, acc);
+        else p.out[r.x] = acc;
+      }
+    }
+    if (!hasN) break;
+    if (hasNN) issue_rec(oaNN, nlocNN, buf);  // own records of the chunk after the next one
+    cp_async_commit();
+    c = cn;
+    cn = cnn;
+    hasN = hasNN;
+    nlocC = nlocN;
+    nlocN = nlocNN;
+    buf ^= 1;
+  }
+#undef GRK
+#undef GPS
+}
+
+template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
+static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
+{
+  using GP = Grp<DIM, G>;
+  constexpr int SPU = (GP::LP + (HANG ? GP::N : 0) + 1) & ~1;
+  if (cs.spu != SPU || (int)cs.elemsPerChunk > TPB) { set_error("internal: group set does not match its kernel"); return DKT_ERR_INVALID; }
+  p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint2 *)cs.d_rec; p.jd = cs.d_jd;
+  p.node_off = cs.d_node_off; p.lev = cs.lev; p.fmask64 = cs.fmask64;
+  p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
+  p.xcap = (uint32_t)cs.elemsPerChunk * SPU + 258u;  // + padding of the first 16 diagonals + the trash position
+  p.ncap = (cs.maxNloc + 2) & ~1u;
+  p.jdStride = cs.jdStride;
+  const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.ncap * sizeof(uint2) +
+                      2 * (size_t)p.jdStride * sizeof(int);
+  auto kern = k_mvg<DIM, G, OPKIND, DIRI, HANG, TPB>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TPB, smem));
+  if (perSM < 1) { set_error("group kernel does not fit on an SM"); return DKT_ERR_CUDA; }
+  const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * da.numSMs));
+  DKT_LAUNCH(kern, grid, TPB, smem, da.stream)(p);
+  g_launches++;
+  return DKT_OK;
+}
+
+template <int DIM, int ORDER, int OPKIND, bool DIRI>
+static int launch_group(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
+{
+  if constexpr (ORDER == 1 && (OPKIND == DKT_OP_IDENTITY || OPKIND == OP_HADAMARD))
+  {
+    const bool hang = cs.rows == 2;
+#define GRP_CASE(D, GG, TR, TH)                                                              \
+  if constexpr (DIM == D)                                                                    \
+  {                                                                                          \
+    if (cs.g == GG)                                                                          \
+      return hang ? launch_group_one<DIM, GG, OPKIND, DIRI, true, TH>(da, cs, p)             \
+                  : launch_group_one<DIM, GG, OPKIND, DIRI, false, TR>(da, cs, p);           \
+  }
+    GRP_CASE(4, 2, 128, 96)
+#ifdef DKT_GROUPS_G3
+    GRP_CASE(4, 3, 96, 96)
+#endif
+    GRP_CASE(3, 3, 128, 128)
+    GRP_CASE(2, 2, 128, 128)
+#undef GRP_CASE
+  }
+  set_error("internal: no sibling-group kernel for this (dim, g, operator)");
+  return DKT_ERR_UNSUPPORTED;
 }
 
 template <int DIM, int ORDER, int OPKIND, bool DIRI>
@@ -944,20 +1703,19 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
   for (const ChunkSet &cs : da.sets)
   {
     if (!cs.nChunks || !((phaseMask >> cs.phase) & 1u)) continue;
-    const uint8_t *lev = da.d_mv_lev + cs.elem0, *child = da.d_mv_child + cs.elem0;
-    p.fmask = da.d_fmask ? da.d_fmask + cs.hang0 : nullptr;
     int rc = DKT_OK;
-    if (cs.rows == 1)
+    if (cs.kind == 1) rc = launch_group<DIM, ORDER, OPKIND, DIRI>(da, cs, p);
+    else if (cs.rows == 1)
     {
-      if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p, lev, child);
-      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, cs, p, lev, child);
+      if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, cs, p);
     }
     else if (cs.maxNloc <= 8u * TPB_H)
     {
-      if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, cs, p, lev, child);
-      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, cs, p, lev, child);
+      if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, cs, p);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, cs, p);
     }
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, cs, p, lev, child);
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, cs, p);
     if (rc) return rc;
   }
   CK(cudaGetLastError());
@@ -1025,6 +1783,8 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
       }
     }
   }
+  if (da.groups && !((hadamard || op->kind == DKT_OP_IDENTITY) && p.exact_ip))
+    return run_matvec(da, op, d_in, d_out, scale, flags);  // group tables serve the fast forms only (DKT_GROUPS is opt-in)
   if (zeroOut)
   {
     CK(cudaMemsetAsync(d_out, 0, da.nNodes * sizeof(double), da.stream));

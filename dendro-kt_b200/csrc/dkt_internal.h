@@ -34,7 +34,7 @@ extern uint64_t g_launches;
 // One set of element chunks for the shared-memory matvec (dkt_chunks.cu).
 struct ChunkSet
 {
-  int rows = 1;                  // slot rows per element: 1 regular, 2 hanging (own + parent lattice)
+  int rows = 1;                  // 1 regular, 2 hanging (per-element sets: slot rows = own + parent lattice)
   int phase = 0;                 // partitioned DA: 0 interior (first half), 1 boundary, 2 interior (second half)
   uint64_t elem0 = 0;            // first visited element of the set (index into d_mv_*, d_e2n)
   uint64_t hang0 = 0;            // hanging sets: first hanging-local element (index into d_pnode, d_fmask)
@@ -47,6 +47,17 @@ struct ChunkSet
   uint16_t *d_meta = nullptr;    // [totalNodes] run length | boundary bit | shared bit
   uint16_t *d_jd = nullptr;      // [nChunks*jdStride] jagged-diagonal offsets
   uint64_t *d_node_off = nullptr;// [nChunks+1]
+  // per-unit attributes (the DA's own arrays, or copies listed in `owned`)
+  const uint8_t *lev = nullptr;    // level
+  const uint8_t *child = nullptr;  // per-element sets: Morton child number
+  const uint32_t *fmask = nullptr; // hanging per-element sets: filled own slots
+  // sibling-group sets (kind == 1, see dkt_chunks.cu): one unit = 2^g leaves of a complete family
+  int kind = 0, g = 0;
+  int spu = 0;                     // slots per unit (padded to an even number for group sets)
+  uint16_t *d_rk16 = nullptr, *d_ps16 = nullptr;  // node rank / position of every slot, two slots per 32-bit word
+  void *d_rec = nullptr;           // [totalNodes] {gid, meta} (uint2)
+  const uint64_t *fmask64 = nullptr; // hanging group sets: filled own lattice slots
+  std::vector<void *> owned;       // device buffers freed with the set
 };
 
 // Everything one rank needs on the device.  All d_* pointers are device memory.
@@ -90,6 +101,7 @@ struct DA
   uint64_t nRegInterior = 0, nHangInterior = 0;
   bool phased = false;
   int commSMs = 0;                 // SMs left to the NCCL kernels during the interior phases
+  int groups = 0;                  // DKT_GROUPS=g at construction: sibling-group sets in use (single rank, order 1)
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)

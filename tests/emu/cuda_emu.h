@@ -1,0 +1,199 @@
+// Minimal CUDA-on-CPU emulation used ONLY by the CPU test-suite (tests/test_emu_chunks.py) to execute the
+// table-building and matvec kernels of dendro-kt_b200/csrc/dkt_chunks.cu without a GPU.  It is test
+// infrastructure: the product (libdkt.so) is never built with DKT_EMU and has no CPU path.
+//
+// Model: the threads of one block are fibers (ucontext) on one OS thread; __syncthreads() yields to a
+// scheduler that resumes every live fiber once per barrier phase.  The order in which the fibers of a phase
+// run is selectable (forward / reverse / shuffled, env DKT_EMU_ORDER=0/1/2) so that a missing barrier shows
+// up as an order-dependent result.  Blocks run one after the other.  Only what dkt_chunks.cu uses exists.
+#ifndef DKT_CUDA_EMU_H
+#define DKT_CUDA_EMU_H
+
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <random>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __restrict__
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+typedef int cudaError_t;
+#ifndef DKT_INTERNAL_H
+typedef struct CUstream_st *cudaStream_t;
+#endif
+constexpr cudaError_t cudaSuccess = 0;
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+
+namespace emu
+{
+struct Fiber
+{
+  ucontext_t ctx;
+  char *stack = nullptr;
+  bool done = false;
+};
+struct State
+{
+  ucontext_t sched;
+  std::vector<Fiber> fibers;
+  int current = -1;
+  std::function<void()> body;
+  char *dyn_smem = nullptr;
+  size_t dyn_cap = 0;
+  int order = 0;
+  std::mt19937 rng{12345};
+  uint64_t barriers = 0;
+};
+State &state();
+void yield();
+void run_block(unsigned nthreads, const std::function<void()> &body);
+
+template <typename F>
+struct Launch
+{
+  F f;
+  unsigned grid, block;
+  size_t smem;
+  template <typename... A>
+  void operator()(A... args)
+  {
+    State &s = state();
+    if (smem > s.dyn_cap)
+    {
+      free(s.dyn_smem);
+      s.dyn_smem = (char *)aligned_alloc(128, (smem + 127) & ~(size_t)127);
+      s.dyn_cap = smem;
+    }
+    gridDim.x = grid;
+    blockDim.x = block;
+    for (unsigned b = 0; b < grid; b++)
+    {
+      blockIdx.x = b;
+      if (s.dyn_smem) memset(s.dyn_smem, 0xA5, s.dyn_cap);  // poison: shared memory is not zero-initialised
+      run_block(block, [&]() { f(args...); });
+    }
+  }
+};
+template <typename F>
+Launch<F *> make_launch(F *f, uint64_t grid, unsigned block, size_t smem) { return Launch<F *>{f, (unsigned)grid, block, smem}; }
+}  // namespace emu
+
+#define DKT_LAUNCH(k, g, b, s, st) ::emu::make_launch(k, (g), (b), (s))
+#define DKT_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(::emu::state().dyn_smem)
+
+inline void __syncthreads() { emu::yield(); }
+
+template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+using std::max;
+using std::min;
+
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <typename T> inline cudaError_t cudaMalloc(T **p, size_t bytes)
+{
+  *p = (T *)aligned_alloc(256, (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255);
+  if (*p) memset((void *)*p, 0xCD, bytes);  // device memory is not zero-initialised
+  return *p ? cudaSuccess : 2;
+}
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+template <typename K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 3; return cudaSuccess; }  // 3 "SMs": persistent loops iterate
+
+// ---- the two cub block primitives dkt_chunks.cu uses (blocked arrangement, stable LSD radix semantics) ----
+namespace cub
+{
+template <typename Key, int THREADS, int ITEMS, typename Value = char>
+struct BlockRadixSort
+{
+  struct TempStorage
+  {
+    Key k[THREADS * ITEMS];
+    Value v[THREADS * ITEMS];
+  };
+  TempStorage &t;
+  explicit BlockRadixSort(TempStorage &ts) : t(ts) {}
+  void sort_impl(Key *key, Value *val, int b0, int b1)
+  {
+    const int tid = threadIdx.x;
+    for (int i = 0; i < ITEMS; i++)
+    {
+      t.k[tid * ITEMS + i] = key[i];
+      if (val) t.v[tid * ITEMS + i] = val[i];
+    }
+    emu::yield();
+    if (tid == 0)
+    {
+      std::vector<int> idx(THREADS * ITEMS);
+      for (int i = 0; i < THREADS * ITEMS; i++) idx[i] = i;
+      const uint64_t mask = (b1 - b0 >= 64) ? ~0ull : ((1ull << (b1 - b0)) - 1);
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+        return (((uint64_t)t.k[a] >> b0) & mask) < (((uint64_t)t.k[b] >> b0) & mask);
+      });
+      std::vector<Key> kk(THREADS * ITEMS);
+      std::vector<Value> vv(THREADS * ITEMS);
+      for (int i = 0; i < THREADS * ITEMS; i++) { kk[i] = t.k[idx[i]]; vv[i] = t.v[idx[i]]; }
+      for (int i = 0; i < THREADS * ITEMS; i++) { t.k[i] = kk[i]; t.v[i] = vv[i]; }
+    }
+    emu::yield();
+    for (int i = 0; i < ITEMS; i++)
+    {
+      key[i] = t.k[tid * ITEMS + i];
+      if (val) val[i] = t.v[tid * ITEMS + i];
+    }
+  }
+  void Sort(Key (&key)[ITEMS], Value (&val)[ITEMS], int b0 = 0, int b1 = sizeof(Key) * 8) { sort_impl(key, val, b0, b1); }
+  void Sort(Key (&key)[ITEMS], int b0 = 0, int b1 = sizeof(Key) * 8) { sort_impl(key, nullptr, b0, b1); }
+};
+template <typename T, int THREADS>
+struct BlockScan
+{
+  struct TempStorage
+  {
+    T v[THREADS + 1];
+  };
+  TempStorage &t;
+  explicit BlockScan(TempStorage &ts) : t(ts) {}
+  void ExclusiveSum(T in, T &out, T &total)
+  {
+    const int tid = threadIdx.x;
+    t.v[tid] = in;
+    emu::yield();
+    T acc = 0;
+    for (int i = 0; i < tid; i++) acc += t.v[i];
+    T tot = 0;
+    for (int i = 0; i < THREADS; i++) tot += t.v[i];
+    emu::yield();
+    out = acc;
+    total = tot;
+  }
+};
+}  // namespace cub
+
+#endif

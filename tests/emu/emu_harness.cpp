@@ -1,0 +1,88 @@
+// Host entry of the emulated chunk path (tests only): fills a dkt::DA from tables the ORACLE built
+// (oracle/flat.py), runs dkt_chunks.cu's build_chunks + run_matvec_chunked under tests/emu/cuda_emu.h and
+// returns the vector.  Nothing here is linked into libdkt.so.
+#include "dkt_internal.h"
+#include "cuda_emu.h"
+
+#include <string>
+
+namespace dkt
+{
+static std::string g_err;
+uint64_t g_launches = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+int device_exclusive_scan(DA &, const uint64_t *in, uint64_t *out, uint64_t n)
+{
+  uint64_t acc = 0;
+  for (uint64_t i = 0; i < n; i++)
+  {
+    const uint64_t v = in[i];
+    out[i] = acc;
+    acc += v;
+  }
+  return DKT_OK;
+}
+// the flat kernels are not part of the emulated build
+int run_matvec(DA &, const dkt_op *, const double *, double *, double, unsigned)
+{
+  set_error("emulation: flat fallback requested");
+  return DKT_ERR_UNSUPPORTED;
+}
+}  // namespace dkt
+
+template <typename T>
+static T *dup(const T *src, size_t n)
+{
+  T *p = (T *)malloc(std::max<size_t>(n, 1) * sizeof(T));
+  if (src && n) memcpy(p, src, n * sizeof(T));
+  return p;
+}
+
+extern "C" const char *emu_last_error() { return dkt::g_err.c_str(); }
+
+// info: per set 8 numbers {kind, rows, g, units, chunks, units per chunk, max nodes per chunk, total chunk nodes}, up to 8 sets
+extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint64_t nReg, uint64_t nNodes, const uint32_t *e2n,
+                          const uint32_t *pnode, const uint32_t *mv_xyz, const uint8_t *mv_lev, const uint32_t *mv_src,
+                          const uint8_t *isbdy, const double *ip0, const double *ip1, int op_kind, const double *kref, double alpha,
+                          int dirichlet, const double *in, double *out, double scale, unsigned flags, uint64_t *info)
+{
+  using namespace dkt;
+  DA da;
+  da.dim = dim; da.order = order; da.max_depth = max_depth;
+  da.M = order + 1;
+  da.N = 1;
+  for (int i = 0; i < dim; i++) da.N *= da.M;
+  da.nMv = nMv; da.nReg = nReg; da.nHang = nMv - nReg; da.nNodes = nNodes; da.nElem = nMv;
+  const int N = da.N;
+  da.d_e2n = dup(e2n, nMv * N);
+  da.d_pnode = dup(pnode, da.nHang * N);
+  da.d_mv_xyz = dup(mv_xyz, nMv * dim);
+  da.d_mv_lev = dup(mv_lev, nMv);
+  da.d_mv_src = dup(mv_src, nMv);
+  da.d_node_isbdy = dup(isbdy, nNodes);
+  for (int i = 0; i < da.M * da.M; i++) { da.ip[0][i] = ip0[i]; da.ip[1][i] = ip1[i]; }
+  int rc = build_chunks(da);
+  if (rc == DKT_OK)
+  {
+    for (int i = 0; i < 64; i++) info[i] = 0;
+    size_t k = 0;
+    for (const ChunkSet &cs : da.sets)
+    {
+      if (k >= 8) break;
+      uint64_t *o = info + 8 * k++;
+      o[0] = cs.kind; o[1] = cs.rows; o[2] = cs.g; o[3] = cs.nElem; o[4] = cs.nChunks; o[5] = cs.elemsPerChunk; o[6] = cs.maxNloc;
+      o[7] = cs.totalNodes;
+    }
+    dkt_op op;
+    op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+    double *din = dup(in, nNodes), *dout = dup((const double *)nullptr, nNodes);
+    rc = run_matvec_chunked(da, &op, din, dout, scale, flags);
+    memcpy(out, dout, nNodes * sizeof(double));
+    free(din);
+    free(dout);
+  }
+  free_chunks(da);
+  free(da.d_e2n); free(da.d_pnode); free(da.d_mv_xyz); free(da.d_mv_lev); free(da.d_mv_src); free(da.d_node_isbdy);
+  return rc;
+}
+extern "C" void emu_set_order(int order) { emu::state().order = order; }

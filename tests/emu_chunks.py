@@ -1,0 +1,90 @@
+"""Python side of the CUDA-on-CPU emulation of dkt_chunks.cu (tests/emu/): builds libdkt_emu.so with g++ and
+feeds it the ORACLE's flat tables.  Test infrastructure only - see tests/emu/cuda_emu.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "dendro-kt_b200", "csrc")
+LIB = os.path.join(EMU, "_build", "libdkt_emu.so")
+INVALID = 0xFFFFFFFF
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(CSRC, "dkt_chunks.cu"), os.path.join(EMU, "cuda_emu.cpp"), os.path.join(EMU, "emu_harness.cpp")]
+    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(ROOT, "include", "dkt.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-shared", "-fPIC",
+           "-x", "c++"] + srcs + ["-o", LIB]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None, dirichlet=False, groups=0, flags=0, order=0):
+    """Emulated dkt chunk path on the oracle's FlatTables `t`.  Returns (v, sets) where sets lists
+    (kind, rows, g, units, chunks, units per chunk, max nodes per chunk, total chunk nodes)."""
+    import flat
+    dim, N = t.dim, t.N
+    nMv = len(t.mv_lev)
+    hang = np.zeros(nMv, dtype=bool)
+    hang[t.hang_idx] = True
+    perm = np.concatenate([np.nonzero(~hang)[0], np.nonzero(hang)[0]])  # regular first, hanging after (dkt_build.cu)
+    nReg = int((~hang).sum())
+    e2n = np.ascontiguousarray(np.where(t.e2n < 0, INVALID, t.e2n)[perm].astype(np.uint32))
+    hpos = np.full(nMv, -1, dtype=np.int64)
+    hpos[t.hang_idx] = np.arange(len(t.hang_idx))
+    pn = t.pnode[hpos[perm[nReg:]]] if len(t.hang_idx) else np.zeros((0, N), dtype=np.int64)
+    pnode = np.ascontiguousarray(np.where(pn < 0, INVALID, pn).astype(np.uint32))
+    xyz = np.ascontiguousarray(t.mv_xyz[perm].astype(np.uint32))
+    lev = np.ascontiguousarray(t.mv_lev[perm].astype(np.uint8))
+    src = np.ascontiguousarray(perm.astype(np.uint32))
+    nNodes = len(t.node_lev)
+    isbdy = np.zeros(nNodes, dtype=np.uint8)
+    isbdy[t.bdy_ids] = 1
+    if ip0 is None:
+        ip0, ip1 = flat.default_interp(t.order)
+    ip0 = np.ascontiguousarray(np.asarray(ip0, dtype=np.float64).ravel())
+    ip1 = np.ascontiguousarray(np.asarray(ip1, dtype=np.float64).ravel())
+    kr = None if kref is None else np.ascontiguousarray(np.asarray(kref, dtype=np.float64).ravel())
+    u = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
+    out = np.full(nNodes, np.nan)
+    info = np.zeros(64, dtype=np.uint64)
+    old = {k: os.environ.get(k) for k in ("DKT_GROUPS", "DKT_EMU_ORDER")}
+    os.environ["DKT_GROUPS"] = str(groups)
+    os.environ["DKT_EMU_ORDER"] = str(order)
+    try:
+        L = lib()
+        # the fiber order is read once per process: set it through the exported state instead
+        L.emu_set_order(C.c_int(order))
+        rc = L.emu_matvec(C.c_int(dim), C.c_int(t.order), C.c_int(max_depth), C.c_uint64(nMv), C.c_uint64(nReg), C.c_uint64(nNodes),
+                          _p(e2n), _p(pnode), _p(xyz), _p(lev), _p(src), _p(isbdy), _p(ip0), _p(ip1),
+                          C.c_int(0 if kr is None else 1), None if kr is None else _p(kr), C.c_double(alpha), C.c_int(int(dirichlet)),
+                          _p(u), _p(out), C.c_double(scale), C.c_uint(flags), _p(info))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if rc != 0:
+        raise RuntimeError("emu_matvec rc=%d: %s" % (rc, L.emu_last_error().decode()))
+    sets = [tuple(int(x) for x in info[8 * i:8 * i + 8]) for i in range(8) if info[8 * i + 4]]
+    return out, sets

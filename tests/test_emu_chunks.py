@@ -1,0 +1,84 @@
+"""CPU tests of the chunked matvec's LOGIC: dendro-kt_b200/csrc/dkt_chunks.cu is compiled with g++ against
+tests/emu/cuda_emu.h (threads of a block = fibers, see there) and its table construction + kernels are run on
+the oracle's element->node tables, then compared with the golden vectors taken from the reference and with the
+oracle.  This covers the per-element sets (the production default) and the opt-in sibling-group sets
+(DKT_GROUPS) without a GPU; it says nothing about performance and is not a CPU path of the product."""
+import numpy as np
+import pytest
+
+import cases
+import emu_chunks
+import flat
+from test_oracle import load_case
+
+ORDER1 = [c for c in cases.ALL_CASES if "-p1-" in c]
+ORDER2 = ["ex1-d2-p2-morton-4", "ex3-d3-p2-morton-3", "gauss-d3-p2-morton"]
+GROUP_G = {2: 2, 3: 3, 4: 2}
+TOL = 1e-12  # BASELINE.json: output vectors within 1e-12 relative
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def _tables(name):
+    case = load_case(name)
+    return case, case["golden"], cases.oracle_tables_for(case)
+
+
+@pytest.mark.parametrize("name", ORDER1 + ORDER2)
+def test_emulated_element_sets_match_reference(name):
+    """default tables (one unit per element), dense operator / Dirichlet / identity against the golden vectors"""
+    case, g, t = _tables(name)
+    n = len(g["node_lev"])
+    K = cases.dense_operator(case["dim"], case["order"])
+    u = cases.input_vector(n)
+    kw = dict(alpha=float(g["alpha"]), scale=float(g["scale"]), ip0=g["ip0"], ip1=g["ip1"])
+    big = len(t.mv_lev) > 50000
+    v, sets = emu_chunks.matvec(t, u, case["max_depth"], kref=K, **kw)
+    assert all(s[0] == 0 for s in sets)
+    assert rel(v, g["v_dense"]) <= TOL
+    if not big:
+        v, _ = emu_chunks.matvec(t, u, case["max_depth"], kref=K, dirichlet=True, order=2, **kw)
+        assert rel(v, g["v_dense_diri"]) <= TOL
+        v, _ = emu_chunks.matvec(t, np.ones(n), case["max_depth"], ip0=g["ip0"], ip1=g["ip1"], order=1)
+        assert rel(v, g["v_id"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ORDER1)
+def test_emulated_group_sets_match_reference(name):
+    """sibling-group tables + group kernels: identity against the reference's golden vector, Walsh-Hadamard
+    Laplacian (+ Dirichlet) against the oracle; every fiber order must give the same vector"""
+    case, g, t = _tables(name)
+    dim, md = case["dim"], case["max_depth"]
+    gg = GROUP_G[dim]
+    n = len(g["node_lev"])
+    big = len(t.mv_lev) > 50000
+    v, sets = emu_chunks.matvec(t, np.ones(n), md, ip0=g["ip0"], ip1=g["ip1"], groups=gg)
+    assert rel(v, g["v_id"]) <= TOL
+    # every visited element is in exactly one set
+    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
+    assert units == len(t.mv_lev)
+    K = flat.laplace_kref(dim, 1)
+    u = cases.input_vector(n)
+    for diri in ((False,) if big else (False, True)):
+        ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri)
+        for order in ((2,) if big else (0, 1, 2)):
+            v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri,
+                                     groups=gg, order=order)
+            assert rel(v, ref) <= TOL
+
+
+def test_group_sets_cover_most_of_an_adaptive_tree():
+    """on the benchmark's tree family nearly all leaves sit in complete sibling families"""
+    import dkt
+    xyz, lev = dkt.trees.moving_ball_tree(3, 6, 10)
+    t = flat.build_tables(xyz, lev, 3, 1, 10)
+    u = cases.input_vector(len(t.node_lev))
+    v, sets = emu_chunks.matvec(t, u, 10, groups=3)
+    assert rel(v, flat.matvec(t, u)) <= TOL
+    grouped = sum(s[3] << s[2] for s in sets if s[0] == 1)
+    assert grouped >= 0.9 * len(t.mv_lev)
+    # fewer slots than one per (element, node)
+    slots_grouped = sum(s[3] * (28 if s[1] == 1 else 36) for s in sets if s[0] == 1)
+    assert slots_grouped < 0.5 * grouped * 8
