@@ -497,12 +497,12 @@ __global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_
 }
 
 // ---- sibling groups: discovery ---------------------------------------------------------------
-// d_mv_src is the position of every visited element in the visit (SFC) order; a complete family of leaves
-// is 2^dim consecutive positions with one parent.
-__global__ void k_invert_src(const uint32_t *src, uint64_t n, uint32_t *inv)
+// d_mv_src is the position of every visited element in the visit (SFC) order (minus mv_src0 on a partitioned
+// DA); a complete family of leaves is 2^dim consecutive positions with one parent.
+__global__ void k_invert_src(const uint32_t *src, uint64_t n, uint64_t base, uint32_t *inv)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) inv[src[i]] = (uint32_t)i;
+  if (i < n) inv[src[i] - base] = (uint32_t)i;
 }
 __global__ void k_family_heads(const uint32_t *inv, const uint32_t *xyz, const uint8_t *lev, uint64_t n, int dim, int max_depth,
                                uint64_t *head)
@@ -534,7 +534,7 @@ __global__ void k_family_heads(const uint32_t *inv, const uint32_t *xyz, const u
         }
         seen |= 1u << c;
       }
-      h = (ok && seen == (nch == 32 ? 0xFFFFFFFFu : ((1u << nch) - 1u))) ? 1 : 0;
+      h = (ok && seen == ((1u << nch) - 1u)) ? 1 : 0;
     }
   }
   head[j] = h;
@@ -554,37 +554,51 @@ __global__ void k_family_members(const uint32_t *inv, const uint64_t *head, cons
     infam[b] = 1;
   }
 }
-// group (f, cR) is hanging if one of its 2^g members is
-__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, uint64_t nReg, uint64_t *ghang)
+// class of a unit: bit 1 = hanging, bit 0 = boundary (touches a ghost node; partitioned DA with comm/compute overlap).
+// A group is hanging / boundary if one of its 2^g members is.
+__device__ __forceinline__ int elem_class(uint64_t e, uint64_t nReg, uint64_t nRegInt, uint64_t nHangInt, int phased)
 {
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u > nGroups) return;
-  if (u == nGroups) { ghang[u] = 0; return; }
-  const int NR = 1 << (dim - g), NC = 1 << g;
-  const uint64_t f = u / NR;
-  const int cR = (int)(u % NR);
-  uint64_t h = 0;
-  for (int cG = 0; cG < NC; cG++)
-    if (mem[(f << dim) + ((cR << g) | cG)] >= nReg) h = 1;
-  ghang[u] = h;
+  const int hang = e >= nReg;
+  const int bdy = phased && (hang ? (e - nReg >= nHangInt) : (e >= nRegInt));
+  return (hang << 1) | bdy;
 }
-// member lists of the regular / hanging groups, both in (family, cR) order
-__global__ void k_group_lists(const uint32_t *mem, const uint64_t *ghang, const uint64_t *hpos, uint64_t nGroups, int dim, int g,
-                              uint32_t *listR, uint32_t *listH)
+__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, uint64_t nReg, uint64_t nRegInt, uint64_t nHangInt,
+                              int phased, uint8_t *cls)
 {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= nGroups) return;
   const int NR = 1 << (dim - g), NC = 1 << g;
   const uint64_t f = u / NR;
   const int cR = (int)(u % NR);
-  uint32_t *dst = ghang[u] ? listH + hpos[u] * NC : listR + (u - hpos[u]) * NC;
-  for (int cG = 0; cG < NC; cG++) dst[cG] = mem[(f << dim) + ((cR << g) | cG)];
+  int c = 0;
+  for (int cG = 0; cG < NC; cG++) c |= elem_class(mem[(f << dim) + ((cR << g) | cG)], nReg, nRegInt, nHangInt, phased);
+  cls[u] = (uint8_t)c;
 }
-__global__ void k_single_flags(const uint8_t *infam, uint64_t n, uint64_t lo, uint64_t hi, uint64_t *flag)
+// the elements outside complete families: class as above, 255 for family members
+__global__ void k_single_class(const uint8_t *infam, uint64_t n, uint64_t nReg, uint64_t nRegInt, uint64_t nHangInt, int phased,
+                               uint8_t *cls)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cls[i] = infam[i] ? (uint8_t)255 : (uint8_t)elem_class(i, nReg, nRegInt, nHangInt, phased);
+}
+__global__ void k_class_flags(const uint8_t *cls, uint64_t n, int want, uint64_t *flag)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i > n) return;
-  flag[i] = (i < n && i >= lo && i < hi && !infam[i]) ? 1 : 0;
+  flag[i] = (i < n && cls[i] == want) ? 1 : 0;
+}
+// member lists of the selected groups, in (family, cR) order
+__global__ void k_group_list(const uint32_t *mem, const uint64_t *flag, const uint64_t *pos, uint64_t nGroups, int dim, int g,
+                             uint32_t *list)
+{
+  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (u >= nGroups || !flag[u]) return;
+  const int NR = 1 << (dim - g), NC = 1 << g;
+  const uint64_t f = u / NR;
+  const int cR = (int)(u % NR);
+  uint32_t *dst = list + pos[u] * NC;
+  for (int cG = 0; cG < NC; cG++) dst[cG] = mem[(f << dim) + ((cR << g) | cG)];
 }
 __global__ void k_compact(const uint64_t *flag, const uint64_t *pos, uint64_t n, uint32_t *list)
 {
@@ -689,15 +703,15 @@ static int add_elem_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *e
   return DKT_OK;
 }
 
-static int add_group_set(DA &da, std::vector<PendingSet> &pend, uint32_t *list, uint64_t n, int g, int hang)
+static int add_group_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *list, uint64_t n, int g, int hang, int phase)
 {
-  if (n == 0) { cudaFree(list); return DKT_OK; }
+  if (n == 0) return DKT_OK;
   da.sets.emplace_back();
   ChunkSet &cs = da.sets.back();
   int L3 = 1;
   for (int d = 0; d < g; d++) L3 *= 3;
   const int LP = L3 << (da.dim - g);
-  cs.rows = hang ? 2 : 1; cs.phase = 0; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
+  cs.rows = hang ? 2 : 1; cs.phase = phase; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
   cs.spu = (LP + (hang ? da.N : 0) + 1) & ~1;
   cs.elemsPerChunk = std::min(SLOT_CAP_GRP / cs.spu, GRP_TPB);
   uint32_t *U = nullptr;
@@ -711,9 +725,42 @@ static int add_group_set(DA &da, std::vector<PendingSet> &pend, uint32_t *list, 
                                                                         da.d_mv_lev, U, lev_g, fm);
   g_launches++;
   cs.lev = lev_g; cs.fmask64 = (const uint64_t *)fm;
-  cs.owned.push_back(lev_g); cs.owned.push_back(fm); cs.owned.push_back(list);
+  cs.owned.push_back(lev_g); cs.owned.push_back(fm);
   pend.push_back({da.sets.size() - 1, U});
   return DKT_OK;
+}
+
+// per-element set of the elements in `list` (outside complete families): compact copies of their rows
+static int add_single_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *list, uint64_t nS, int hang, int phase)
+{
+  if (nS == 0) return DKT_OK;
+  const int N = da.N;
+  uint32_t *e2n_s = nullptr, *pnode_s = nullptr, *fm_s = nullptr;
+  uint8_t *lev_s = nullptr, *child_s = nullptr;
+  CK(cudaMalloc((void **)&e2n_s, nS * N * sizeof(uint32_t)));
+  if (hang) CK(cudaMalloc((void **)&pnode_s, nS * N * sizeof(uint32_t)));
+  if (hang) CK(cudaMalloc((void **)&fm_s, nS * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&lev_s, nS));
+  CK(cudaMalloc((void **)&child_s, nS));
+  DKT_LAUNCH(k_gather_single, nblk(nS), 256, 0, da.stream)(list, nS, N, da.nReg, da.d_e2n, da.d_pnode, da.d_mv_lev, da.d_mv_child, e2n_s,
+                                                           pnode_s, lev_s, child_s);
+  g_launches++;
+  if (hang)
+  {
+    DKT_LAUNCH(k_fmask, nblk(nS), 256, 0, da.stream)(e2n_s, child_s, nS, N, da.order == 1 ? 1 : 0, fm_s);
+    g_launches++;
+  }
+  int rc = add_elem_set(da, pend, e2n_s, pnode_s, lev_s, child_s, fm_s, nS, hang ? 2 : 1, phase, 0, 0);
+  if (rc == DKT_OK)
+  {
+    ChunkSet &cs = da.sets.back();
+    cs.owned.push_back(lev_s); cs.owned.push_back(child_s);
+    if (fm_s) cs.owned.push_back(fm_s);
+  }
+  CK(cudaStreamSynchronize(da.stream));
+  cudaFree(e2n_s);
+  cudaFree(pnode_s);
+  return rc;
 }
 
 // DKT_GROUPS=g: group the leaves of complete sibling families (see the file header).  0 / unset: off.
@@ -722,7 +769,7 @@ static int groups_requested(const DA &da)
   const char *e = getenv("DKT_GROUPS");
   if (!e) return 0;
   const int g = atoi(e);
-  if (g <= 0 || da.order != 1 || da.phased || g > da.dim) return 0;
+  if (g <= 0 || da.order != 1 || g > da.dim) return 0;
   if (!((da.dim == 4 && (g == 2 || g == 3)) || (da.dim == 3 && g == 3) || (da.dim == 2 && g == 2))) return 0;
   return g;
 }
@@ -775,15 +822,17 @@ int build_chunks(DA &da)
   {
     const uint64_t n = da.nMv;
     const int nch = 1 << da.dim, NC = 1 << g, NR = 1 << (da.dim - g);
+    const int phased = da.phased ? 1 : 0;
     uint32_t *inv = nullptr, *mem = nullptr;
     uint64_t *flag = nullptr, *pos = nullptr;
-    uint8_t *infam = nullptr;
+    uint8_t *infam = nullptr, *cls = nullptr;
     CK(cudaMalloc((void **)&inv, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&flag, (n + 1) * sizeof(uint64_t)));
     CK(cudaMalloc((void **)&pos, (n + 1) * sizeof(uint64_t)));
     CK(cudaMalloc((void **)&infam, std::max<uint64_t>(n, 1)));
+    CK(cudaMalloc((void **)&cls, std::max<uint64_t>(n, 1)));
     CK(cudaMemsetAsync(infam, 0, std::max<uint64_t>(n, 1), da.stream));
-    DKT_LAUNCH(k_invert_src, nblk(n), 256, 0, da.stream)(da.d_mv_src, n, inv);
+    DKT_LAUNCH(k_invert_src, nblk(n), 256, 0, da.stream)(da.d_mv_src, n, da.mv_src0, inv);
     DKT_LAUNCH(k_family_heads, nblk(n + 1), 256, 0, da.stream)(inv, da.d_mv_xyz, da.d_mv_lev, n, da.dim, da.max_depth, flag);
     g_launches += 2;
     uint64_t nFam = 0;
@@ -792,65 +841,72 @@ int build_chunks(DA &da)
     CK(cudaMalloc((void **)&mem, std::max<uint64_t>(nFam, 1) * nch * sizeof(uint32_t)));
     DKT_LAUNCH(k_family_members, nblk(n), 256, 0, da.stream)(inv, flag, pos, da.d_mv_child, n, da.dim, mem, infam);
     g_launches++;
-    // groups -> regular / hanging lists
+    std::vector<uint32_t *> lists;  // freed after the unit slot tables are built
+    // interior units run in two halves around the boundary ones (see run_matvec_dist); unpartitioned: one set
+    auto add_sets = [&](const uint32_t *list, uint64_t cnt, int width, int c, bool group) -> int {
+      const int hang = (c >> 1) & 1, bdy = c & 1;
+      struct Sub { uint64_t a, b; int phase; };
+      std::vector<Sub> subs;
+      if (!phased) subs = {{0, cnt, 0}};
+      else if (bdy) subs = {{0, cnt, 1}};
+      else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
+      for (const Sub &s : subs)
+      {
+        const int r = group ? add_group_set(da, pend, list + s.a * width, s.b - s.a, g, hang, s.phase)
+                            : add_single_set(da, pend, list + s.a, s.b - s.a, hang, s.phase);
+        if (r) return r;
+      }
+      return DKT_OK;
+    };
+    // groups by class: regular / hanging x interior / boundary
     const uint64_t nGroups = nFam * NR;
-    uint64_t *gh = nullptr, *gpos = nullptr;
-    CK(cudaMalloc((void **)&gh, (nGroups + 1) * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&gpos, (nGroups + 1) * sizeof(uint64_t)));
-    DKT_LAUNCH(k_group_class, nblk(nGroups + 1), 256, 0, da.stream)(mem, nGroups, da.dim, g, da.nReg, gh);
-    g_launches++;
-    uint64_t nGH = 0;
-    rc = scan_total(da, gh, gpos, nGroups, nGH);
-    if (rc) return rc;
-    const uint64_t nGR = nGroups - nGH;
-    uint32_t *listR = nullptr, *listH = nullptr;
-    CK(cudaMalloc((void **)&listR, std::max<uint64_t>(nGR, 1) * NC * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&listH, std::max<uint64_t>(nGH, 1) * NC * sizeof(uint32_t)));
     if (nGroups)
     {
-      DKT_LAUNCH(k_group_lists, nblk(nGroups), 256, 0, da.stream)(mem, gh, gpos, nGroups, da.dim, g, listR, listH);
+      uint64_t *gflag = nullptr, *gpos = nullptr;
+      uint8_t *gcls = nullptr;
+      CK(cudaMalloc((void **)&gflag, (nGroups + 1) * sizeof(uint64_t)));
+      CK(cudaMalloc((void **)&gpos, (nGroups + 1) * sizeof(uint64_t)));
+      CK(cudaMalloc((void **)&gcls, nGroups));
+      DKT_LAUNCH(k_group_class, nblk(nGroups), 256, 0, da.stream)(mem, nGroups, da.dim, g, da.nReg, da.nRegInterior, da.nHangInterior, phased,
+                                                                  gcls);
       g_launches++;
-    }
-    rc = add_group_set(da, pend, listR, nGR, g, 0);
-    if (rc == DKT_OK) rc = add_group_set(da, pend, listH, nGH, g, 1);
-    // the elements outside complete families: compact copies, per-element sets
-    for (int hang = 0; hang < 2 && rc == DKT_OK; hang++)
-    {
-      const uint64_t lo = hang ? da.nReg : 0, hi = hang ? n : da.nReg;
-      DKT_LAUNCH(k_single_flags, nblk(n + 1), 256, 0, da.stream)(infam, n, lo, hi, flag);
-      g_launches++;
-      uint64_t nS = 0;
-      rc = scan_total(da, flag, pos, n, nS);
-      if (rc || !nS) continue;
-      uint32_t *list = nullptr, *e2n_s = nullptr, *pnode_s = nullptr, *fm_s = nullptr;
-      uint8_t *lev_s = nullptr, *child_s = nullptr;
-      CK(cudaMalloc((void **)&list, nS * sizeof(uint32_t)));
-      CK(cudaMalloc((void **)&e2n_s, nS * N * sizeof(uint32_t)));
-      if (hang) CK(cudaMalloc((void **)&pnode_s, nS * N * sizeof(uint32_t)));
-      if (hang) CK(cudaMalloc((void **)&fm_s, nS * sizeof(uint32_t)));
-      CK(cudaMalloc((void **)&lev_s, nS));
-      CK(cudaMalloc((void **)&child_s, nS));
-      DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
-      DKT_LAUNCH(k_gather_single, nblk(nS), 256, 0, da.stream)(list, nS, N, da.nReg, da.d_e2n, da.d_pnode, da.d_mv_lev, da.d_mv_child, e2n_s,
-                                                               pnode_s, lev_s, child_s);
-      g_launches += 2;
-      if (hang)
+      for (int c = 0; c < 4 && rc == DKT_OK; c++)
       {
-        DKT_LAUNCH(k_fmask, nblk(nS), 256, 0, da.stream)(e2n_s, child_s, nS, N, xorperm, fm_s);
+        DKT_LAUNCH(k_class_flags, nblk(nGroups + 1), 256, 0, da.stream)(gcls, nGroups, c, gflag);
         g_launches++;
-      }
-      rc = add_elem_set(da, pend, e2n_s, pnode_s, lev_s, child_s, fm_s, nS, hang ? 2 : 1, 0, 0, 0);
-      if (rc == DKT_OK)
-      {
-        ChunkSet &cs = da.sets.back();
-        cs.owned.push_back(lev_s); cs.owned.push_back(child_s);
-        if (fm_s) cs.owned.push_back(fm_s);
+        uint64_t cnt = 0;
+        rc = scan_total(da, gflag, gpos, nGroups, cnt);
+        if (rc || !cnt) continue;
+        uint32_t *list = nullptr;
+        CK(cudaMalloc((void **)&list, cnt * NC * sizeof(uint32_t)));
+        lists.push_back(list);
+        DKT_LAUNCH(k_group_list, nblk(nGroups), 256, 0, da.stream)(mem, gflag, gpos, nGroups, da.dim, g, list);
+        g_launches++;
+        rc = add_sets(list, cnt, NC, c, true);
       }
       CK(cudaStreamSynchronize(da.stream));
-      cudaFree(list); cudaFree(e2n_s); cudaFree(pnode_s);
+      cudaFree(gflag); cudaFree(gpos); cudaFree(gcls);
+    }
+    // the elements outside complete families, by the same classes
+    DKT_LAUNCH(k_single_class, nblk(n), 256, 0, da.stream)(infam, n, da.nReg, da.nRegInterior, da.nHangInterior, phased, cls);
+    g_launches++;
+    for (int c = 0; c < 4 && rc == DKT_OK; c++)
+    {
+      DKT_LAUNCH(k_class_flags, nblk(n + 1), 256, 0, da.stream)(cls, n, c, flag);
+      g_launches++;
+      uint64_t cnt = 0;
+      rc = scan_total(da, flag, pos, n, cnt);
+      if (rc || !cnt) continue;
+      uint32_t *list = nullptr;
+      CK(cudaMalloc((void **)&list, cnt * sizeof(uint32_t)));
+      lists.push_back(list);
+      DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
+      g_launches++;
+      rc = add_sets(list, cnt, 1, c, false);
     }
     CK(cudaStreamSynchronize(da.stream));
-    cudaFree(inv); cudaFree(mem); cudaFree(flag); cudaFree(pos); cudaFree(infam); cudaFree(gh); cudaFree(gpos);
+    for (uint32_t *l : lists) cudaFree(l);
+    cudaFree(inv); cudaFree(mem); cudaFree(flag); cudaFree(pos); cudaFree(infam); cudaFree(cls);
   }
   // writing references of every node over all sets, then the chunk tables
   uint32_t *refcnt = nullptr;

@@ -512,6 +512,7 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   g.d_e2n = e2nL; g.d_pnode = pnodeL; g.d_mv_xyz = xyzL; g.d_mv_src = srcL; g.d_mv_lev = levL; g.d_child = childL;
   g.d_node_isbdy = bdyL;
   g.nMv = nMvL; g.nReg = nRegL; g.nHang = nHangL;
+  g.mv_src0 = B.b[rank];  // the rank's elements are the visit-order positions [b[rank], b[rank+1])
   g.nNodes = nLocal;  // the chunk tables and the kernels work on the local (owned + ghost) vector
   cudaFree(minsrc); cudaFree(refmask); cudaFree(flag); cudaFree(wide); cudaFree(pos); cudaFree(g2l); cudaFree(l2g);
 

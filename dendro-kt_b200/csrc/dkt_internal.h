@@ -85,6 +85,7 @@ struct DA
   uint32_t *d_mv_xyz = nullptr;    // [nMv*dim]
   uint8_t *d_mv_lev = nullptr;     // [nMv]
   uint32_t *d_mv_src = nullptr;    // [nMv] position in SFC visit order (for export)
+  uint64_t mv_src0 = 0;            // partitioned DA: first visit-order position of this rank (d_mv_src - mv_src0 is a permutation)
   uint32_t *d_pnode = nullptr;     // [nHang*N]
   uint8_t *d_child = nullptr;      // [nHang]
   uint8_t *d_mv_child = nullptr;   // [nMv] Morton child number of every visited element

@@ -44,7 +44,8 @@ extern "C" const char *emu_last_error() { return dkt::g_err.c_str(); }
 extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint64_t nReg, uint64_t nNodes, const uint32_t *e2n,
                           const uint32_t *pnode, const uint32_t *mv_xyz, const uint8_t *mv_lev, const uint32_t *mv_src,
                           const uint8_t *isbdy, const double *ip0, const double *ip1, int op_kind, const double *kref, double alpha,
-                          int dirichlet, const double *in, double *out, double scale, unsigned flags, uint64_t *info)
+                          int dirichlet, const double *in, double *out, double scale, unsigned flags, uint64_t *info, int phased,
+                          uint64_t nRegInt, uint64_t nHangInt, uint64_t src0)
 {
   using namespace dkt;
   DA da;
@@ -61,22 +62,25 @@ extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint6
   da.d_mv_src = dup(mv_src, nMv);
   da.d_node_isbdy = dup(isbdy, nNodes);
   for (int i = 0; i < da.M * da.M; i++) { da.ip[0][i] = ip0[i]; da.ip[1][i] = ip1[i]; }
+  da.phased = phased != 0; da.nRegInterior = nRegInt; da.nHangInterior = nHangInt; da.mv_src0 = src0;
   int rc = build_chunks(da);
   if (rc == DKT_OK)
   {
-    for (int i = 0; i < 64; i++) info[i] = 0;
+    for (int i = 0; i < 128; i++) info[i] = 0;
     size_t k = 0;
     for (const ChunkSet &cs : da.sets)
     {
-      if (k >= 8) break;
+      if (k >= 16) break;
       uint64_t *o = info + 8 * k++;
       o[0] = cs.kind; o[1] = cs.rows; o[2] = cs.g; o[3] = cs.nElem; o[4] = cs.nChunks; o[5] = cs.elemsPerChunk; o[6] = cs.maxNloc;
-      o[7] = cs.totalNodes;
+      o[7] = cs.totalNodes | ((uint64_t)cs.phase << 56);
     }
     dkt_op op;
     op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
     double *din = dup(in, nNodes), *dout = dup((const double *)nullptr, nNodes);
-    rc = run_matvec_chunked(da, &op, din, dout, scale, flags);
+    if (!phased) rc = run_matvec_chunked(da, &op, din, dout, scale, flags);
+    else  // the three phases of run_matvec_dist, without the exchanges
+      for (int ph = 0; ph < 3 && rc == DKT_OK; ph++) rc = run_matvec_chunked(da, &op, din, dout, scale, flags, 1u << ph, ph == 0);
     memcpy(out, dout, nNodes * sizeof(double));
     free(din);
     free(dout);

@@ -82,3 +82,22 @@ def test_group_sets_cover_most_of_an_adaptive_tree():
     # fewer slots than one per (element, node)
     slots_grouped = sum(s[3] * (28 if s[1] == 1 else 36) for s in sets if s[0] == 1)
     assert slots_grouped < 0.5 * grouped * 8
+
+
+@pytest.mark.parametrize("name,groups", [("ball-d3-p1-morton-6", 0), ("ball-d3-p1-morton-6", 3), ("ex3-d4-p1-hilbert-3", 2),
+                                         ("gauss-d4-p1-morton", 2), ("ball-d2-p1-morton-7", 2)])
+def test_emulated_phased_sets(name, groups):
+    """partitioned-DA layout ([interior | boundary] lists, three phases, visit positions with an offset):
+    the phases together must give the single-pass vector"""
+    case, g, t = _tables(name)
+    dim, md = case["dim"], case["max_depth"]
+    n = len(g["node_lev"])
+    K = flat.laplace_kref(dim, 1)
+    u = cases.input_vector(n)
+    ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
+    v, sets = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True,
+                                groups=groups, order=2, phased_seed=11)
+    assert rel(v, ref) <= TOL
+    assert {s[8] for s in sets} == {0, 1, 2}
+    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
+    assert units == len(t.mv_lev)
