@@ -1,0 +1,30 @@
+#!/bin/bash
+# First GPU session of the sibling-group tables (DKT_GROUPS, dkt_chunks.cu k_mvg): parity, then A/B timing, then ncu.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r02_groups_ab.sh'
+# Everything lands in gpurun_out/r02_groups/.
+set -u
+out=gpurun_out/r02_groups
+mkdir -p $out
+python __graft_entry__.py > $out/build.log 2>&1
+DKT_TEST_GROUPS=1 timeout 900 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu > $out/pytest_groups.log 2>&1
+echo "pytest groups rc=$?" | tee -a $out/summary.txt
+for g in 0 2 3; do
+  timeout 600 python bench.py --groups $g --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g$g.json 2> $out/bench_g$g.err
+  echo "bench groups=$g rc=$?" | tee -a $out/summary.txt
+done
+# launch list (per-kernel device time) and one full capture of the group kernels
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_g2.csv \
+  python bench.py --groups 2 --steps 3 --warmup 2 --no-experimental --no-cpu-baseline > $out/ncu_launches.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_mvg -c 4 -o $out/mvg_g2 \
+  python bench.py --groups 2 --steps 2 --warmup 1 --no-experimental --no-cpu-baseline > $out/ncu_full.log 2>&1
+python tools/ncu_summary.py $out/mvg_g2.ncu-rep k_mvg > $out/ncu_mvg_g2.txt 2>&1
+tail -n 3 $out/pytest_groups.log
+for g in 0 2 3; do python - <<PY
+import json
+try:
+    d = json.loads(open("$out/bench_g$g.json").read().strip().splitlines()[-1])
+    print("groups=$g", "ms", round(d["ms_per_step"], 4), "DOF/s %.3e" % d["value"], "frac", round(d["roofline"]["frac"], 4))
+except Exception as e:
+    print("groups=$g", "no result", e)
+PY
+done
