@@ -1737,9 +1737,7 @@ static int launch_group(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
                   : launch_group_one<DIM, GG, OPKIND, DIRI, false, TR>(da, cs, p);           \
   }
     GRP_CASE(4, 2, 128, 96)
-#ifdef DKT_GROUPS_G3
     GRP_CASE(4, 3, 96, 96)
-#endif
     GRP_CASE(3, 3, 128, 128)
     GRP_CASE(2, 2, 128, 128)
 #undef GRP_CASE
