@@ -52,12 +52,14 @@ struct NcclApi
   int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8;
+constexpr int NCCL_UINT8 = 1;
 
 static int load_nccl()
 {
@@ -75,7 +77,7 @@ static int load_nccl()
   if (!g_nccl.field) { set_error(std::string("libnccl lacks ") + name); return DKT_ERR_NCCL; }
   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
   SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-  SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce")
+  SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather")
 #undef SYM
   return DKT_OK;
 }
@@ -242,6 +244,64 @@ __global__ void k_unpack_add(double *v, const uint32_t *idx, uint64_t n, const d
   if (i < n) atomicAdd(v + idx[i], buf[i]);
 }
 
+// ---- peer-memory exchange (DKT_DIST_P2P=1) ---------------------------------------------------------------
+// Every rank owns one IPC-exported buffer  [flagR[64] flagW[64] .. 1 KiB | xr: ghost values, by owner | xw: partial
+// sums coming back, by ghosting rank]  and maps the peers' buffers.  A "put" kernel gathers and stores straight into
+// the peers' receive regions over NVLink (pack + send in one kernel), a one-block kernel then publishes this matvec's
+// epoch in the peers' flag words, and the consumer waits for the epoch right before it needs the data - by then it
+// has normally arrived behind the interior elements.  One stream, no NCCL kernel competing for SMs.
+// Re-use is safe without double buffering: a rank's put of matvec e+1 into a peer follows its wait for that peer's
+// write-back flag of matvec e, which the peer raised after it had consumed the data of matvec e.
+constexpr size_t P2P_FLAG_BYTES = 1024;
+constexpr int P2P_MAX_RANKS = 64;
+__global__ void k_p2p_put(const double *src, const uint32_t *idx, uint64_t n, const uint64_t *seg_off, double *const *peer_dst, int nranks)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int p = 0;
+  while (p + 1 < nranks && i >= seg_off[p + 1]) p++;  // segment of peer p: [seg_off[p], seg_off[p+1])
+  peer_dst[p][i - seg_off[p]] = idx ? src[idx[i]] : src[i];
+  __threadfence_system();
+}
+__global__ void k_p2p_signal(uint32_t *const *peer_flag, const uint64_t *seg_off, int nranks, uint32_t epoch)
+{
+  const int p = threadIdx.x;
+  if (p >= nranks || seg_off[p + 1] == seg_off[p]) return;  // nothing was sent to p
+  __threadfence_system();
+  *(volatile uint32_t *)peer_flag[p] = epoch;
+}
+// every block waits for the epoch of all peers that send to this rank (about 2 s at most, then *err = 1)
+__device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, int *err)
+{
+  const int p = threadIdx.x;
+  if (p < nranks && seg_off[p + 1] != seg_off[p])
+  {
+    const long long t0 = clock64();
+    while ((int32_t)(flags[p] - epoch) < 0)
+    {
+      __nanosleep(100);
+      if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1); break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+__global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
+                                double *dst, uint64_t n, int *err)
+{
+  p2p_wait(flags, seg_off, nranks, epoch, err);
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __ldcg(x + i);
+}
+// several peers may return contributions to the same owned node -> atomic
+__global__ void k_p2p_wait_add(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
+                               double *v, const uint32_t *idx, uint64_t n, int *err)
+{
+  p2p_wait(flags, seg_off, nranks, epoch, err);
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(v + idx[i], __ldcg(x + i));
+}
+
 #define LAUNCHS(kern, n, stream, ...)                                          \
   do                                                                           \
   {                                                                            \
@@ -281,7 +341,82 @@ void free_dist(Dist &d)
   if (d.comm_stream) cudaStreamDestroy(d.comm_stream);
   cudaFree(d.d_send_idx); cudaFree(d.d_send_buf); cudaFree(d.d_recv_buf); cudaFree(d.d_in_local); cudaFree(d.d_out_local);
   cudaFree(d.d_owned_gid);
+  for (void *b : d.peer_base)
+    if (b) cudaIpcCloseMemHandle(b);
+  cudaFree(d.xbuf); cudaFree(d.d_peer_xr); cudaFree(d.d_peer_xw); cudaFree(d.d_peer_flagR); cudaFree(d.d_peer_flagW);
+  cudaFree(d.d_send_off); cudaFree(d.d_recv_off); cudaFree(d.d_p2p_err);
   d = Dist();
+}
+
+// Peer-memory exchange: allocate the exchange buffer, trade IPC handles and segment offsets through the (already
+// initialised) NCCL communicator, map the peers' buffers and build the device pointer tables.
+struct P2PInfo
+{
+  cudaIpcMemHandle_t handle;
+  uint64_t nGhost, totalSend;
+  uint64_t recv_off[P2P_MAX_RANKS + 1], send_off[P2P_MAX_RANKS + 1];
+};
+static int setup_p2p(DA &g, Dist &d)
+{
+  const int R = d.nranks, me = d.rank;
+  if (R > P2P_MAX_RANKS) { set_error("DKT_DIST_P2P: at most 64 ranks"); return DKT_ERR_UNSUPPORTED; }
+  const uint64_t nGhost = d.recv_off[R], totalSend = d.send_off[R];
+  const size_t bytes = P2P_FLAG_BYTES + (nGhost + totalSend + 1) * sizeof(double);
+  CK(cudaMalloc((void **)&d.xbuf, bytes));
+  CK(cudaMemset(d.xbuf, 0, bytes));
+  std::vector<P2PInfo> info(R);
+  P2PInfo &mine = info[me];
+  std::memset(&mine, 0, sizeof(mine));
+  CK(cudaIpcGetMemHandle(&mine.handle, d.xbuf));
+  mine.nGhost = nGhost;
+  mine.totalSend = totalSend;
+  for (int p = 0; p <= R; p++) { mine.recv_off[p] = d.recv_off[p]; mine.send_off[p] = d.send_off[p]; }
+  char *dinfo = nullptr;
+  CK(cudaMalloc((void **)&dinfo, sizeof(P2PInfo) * R));
+  CK(cudaMemcpyAsync(dinfo + sizeof(P2PInfo) * me, &mine, sizeof(P2PInfo), cudaMemcpyHostToDevice, g.stream));
+  NCK(g_nccl.AllGather(dinfo + sizeof(P2PInfo) * me, dinfo, sizeof(P2PInfo), NCCL_UINT8, (ncclComm_p)d.comm, g.stream));
+  CK(cudaMemcpyAsync(info.data(), dinfo, sizeof(P2PInfo) * R, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  cudaFree(dinfo);
+  d.peer_base.assign(R, nullptr);
+  std::vector<double *> xr(R, nullptr), xw(R, nullptr);
+  std::vector<uint32_t *> fr(R, nullptr), fw(R, nullptr);
+  for (int p = 0; p < R; p++)
+  {
+    if (p == me) continue;
+    const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
+    // both sides of every list were derived from the same global tables: they must agree
+    if (info[p].recv_off[me + 1] - info[p].recv_off[me] != sc || info[p].send_off[me + 1] - info[p].send_off[me] != rcv)
+    {
+      set_error("DKT_DIST_P2P: send/receive lists of ranks " + std::to_string(me) + " and " + std::to_string(p) + " disagree");
+      return DKT_ERR_INVALID;
+    }
+    if (!sc && !rcv) continue;
+    void *base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, info[p].handle, cudaIpcMemLazyEnablePeerAccess));
+    d.peer_base[p] = base;
+    double *x = (double *)((char *)base + P2P_FLAG_BYTES);
+    xr[p] = x + info[p].recv_off[me];                    // peer p's ghost values owned by me
+    xw[p] = x + info[p].nGhost + info[p].send_off[me];   // partial sums of p's owned nodes that I ghost
+    fr[p] = (uint32_t *)base + me;
+    fw[p] = (uint32_t *)base + P2P_MAX_RANKS + me;
+  }
+  CK(cudaMalloc((void **)&d.d_peer_xr, R * sizeof(double *)));
+  CK(cudaMalloc((void **)&d.d_peer_xw, R * sizeof(double *)));
+  CK(cudaMalloc((void **)&d.d_peer_flagR, R * sizeof(uint32_t *)));
+  CK(cudaMalloc((void **)&d.d_peer_flagW, R * sizeof(uint32_t *)));
+  CK(cudaMalloc((void **)&d.d_send_off, (R + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&d.d_recv_off, (R + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&d.d_p2p_err, sizeof(int)));
+  CK(cudaMemset(d.d_p2p_err, 0, sizeof(int)));
+  CK(cudaMemcpy(d.d_peer_xr, xr.data(), R * sizeof(double *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.d_peer_xw, xw.data(), R * sizeof(double *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.d_peer_flagR, fr.data(), R * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.d_peer_flagW, fw.data(), R * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.d_send_off, d.send_off.data(), (R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.d_recv_off, d.recv_off.data(), (R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  d.p2p = true;
+  return DKT_OK;
 }
 
 // g: the global single-rank DA (already built, no chunk tables).  On success `g` has been turned into
@@ -524,6 +659,12 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
     ncclComm_p comm = nullptr;
     NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
     dist.comm = comm;
+    const char *e = getenv("DKT_DIST_P2P");
+    if (e && atoi(e) != 0)
+    {
+      rc = setup_p2p(g, dist);
+      if (rc) return rc;
+    }
   }
   {
     int lo = 0, hi = 0;
@@ -532,6 +673,52 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   }
   for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&dist.ev[i], cudaEventDisableTiming));
   dist.active = true;
+  return DKT_OK;
+}
+
+// The same protocol over peer memory (DKT_DIST_P2P=1): everything on the DA's stream.
+static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double *in_local, double *out_local,
+                               double scale, unsigned flags, bool overlap, bool ghosted)
+{
+  cudaStream_t s = da.stream;
+  const int R = d.nranks;
+  const uint64_t nOwned = d.nOwned, totalSend = d.send_off[R], nGhost = d.recv_off[R];
+  const uint32_t epoch = ++d.epoch;
+  double *xr = (double *)(d.xbuf + P2P_FLAG_BYTES), *xw = xr + nGhost;
+  const volatile uint32_t *flagR = (const volatile uint32_t *)d.xbuf, *flagW = flagR + P2P_MAX_RANKS;
+  // readFromGhost: owned values other ranks ghost -> their xr, then publish the epoch
+  LAUNCHS(k_p2p_put, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
+  k_p2p_signal<<<1, P2P_MAX_RANKS, 0, s>>>(d.d_peer_flagR, d.d_send_off, R, epoch);
+  g_launches++;
+  int rc = DKT_OK;
+  if (overlap)
+  {
+    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);  // interior, first half
+    if (rc) return rc;
+  }
+  LAUNCHS(k_p2p_wait_copy, nGhost, s, flagR, d.d_recv_off, R, epoch, xr, in_local + nOwned, nGhost, d.d_p2p_err);
+  if (overlap) rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
+  else rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
+                                  : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
+  if (rc) return rc;
+  // writeToGhosts: ghost partial sums -> the owners' xw, publish, then add what came back for the owned nodes
+  LAUNCHS(k_p2p_put, nGhost, s, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
+  k_p2p_signal<<<1, P2P_MAX_RANKS, 0, s>>>(d.d_peer_flagW, d.d_recv_off, R, epoch);
+  g_launches++;
+  if (overlap)
+  {
+    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);  // interior, second half
+    if (rc) return rc;
+  }
+  LAUNCHS(k_p2p_wait_add, totalSend, s, flagW, d.d_send_off, R, epoch, xw, out_local, d.d_send_idx, totalSend, d.d_p2p_err);
+  if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (getenv("DKT_P2P_CHECK"))
+  {
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, d.d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (err) { set_error("DKT_DIST_P2P: a peer's epoch flag did not arrive within the time limit"); return DKT_ERR_NCCL; }
+  }
   return DKT_OK;
 }
 
@@ -548,6 +735,7 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
   double *out_local = ghosted ? d_out : d.d_out_local;
   if (!ghosted) CK(cudaMemcpyAsync(in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   const bool overlap = d.nranks > 1 && da.phased && !(flags & DKT_MV_FLAT);
+  if (d.p2p && d.nranks > 1) return run_matvec_dist_p2p(da, d, op, d_in, d_out, in_local, out_local, scale, flags, overlap, ghosted);
   cudaStream_t cs = overlap ? d.comm_stream : s;  // the exchanges run beside the interior elements
   if (d.nranks > 1)
   {

@@ -125,6 +125,16 @@ struct Dist
   double *d_send_buf = nullptr, *d_recv_buf = nullptr;
   double *d_in_local = nullptr, *d_out_local = nullptr;  // [owned | ghosts by owner rank]
   uint32_t *d_owned_gid = nullptr;      // global (single-rank DA order) id of each owned node
+  // peer-memory exchange (opt-in DKT_DIST_P2P=1, dkt_dist.cu): kernels store straight into the peers' receive
+  // buffers over NVLink and signal epoch flags; no NCCL kernel, no second stream
+  bool p2p = false;
+  char *xbuf = nullptr;                 // [flags 1 KiB | xr: nGhost doubles | xw: totalSend doubles], IPC-exported
+  std::vector<void *> peer_base;        // the peers' xbuf mapped into this process (nullptr: not needed / self)
+  double **d_peer_xr = nullptr, **d_peer_xw = nullptr;          // [nranks] where this rank's segment starts on peer p
+  uint32_t **d_peer_flagR = nullptr, **d_peer_flagW = nullptr;  // [nranks] this rank's flag on peer p
+  uint64_t *d_send_off = nullptr, *d_recv_off = nullptr;        // device copies [nranks+1]
+  int *d_p2p_err = nullptr;             // set by a wait kernel that timed out
+  uint32_t epoch = 0;
 };
 int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id);
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
