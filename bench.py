@@ -377,7 +377,7 @@ def run_gpu(args):
         if args.experimental and world == 1 and not args.groups:
             # opt-in sibling-group tables (DKT_GROUPS, validated against the oracle in the CPU emulation, tests/test_emu_chunks.py):
             # timed in a separate process AFTER the headline measurement; informational only
-            line["experimental_groups"] = run_groups_probe_subprocess(args)
+            line["experimental_groups"] = [run_groups_probe_subprocess(args, g=2, timeout=150), run_groups_probe_subprocess(args, g=3, timeout=150)]
         print(json.dumps(line))
     da.close()
     if dist is not None:

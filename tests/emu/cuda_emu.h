@@ -77,19 +77,25 @@ struct Launch
   void operator()(A... args)
   {
     State &s = state();
-    if (smem > s.dyn_cap)
-    {
-      free(s.dyn_smem);
-      s.dyn_smem = (char *)aligned_alloc(128, (smem + 127) & ~(size_t)127);
-      s.dyn_cap = smem;
-    }
+    // exactly the requested bytes + a canary behind them: a write past the dynamic shared memory aborts
+    constexpr size_t CANARY = 256;
+    free(s.dyn_smem);
+    s.dyn_smem = (char *)aligned_alloc(128, (smem + CANARY + 127) & ~(size_t)127);
+    s.dyn_cap = smem;
     gridDim.x = grid;
     blockDim.x = block;
     for (unsigned b = 0; b < grid; b++)
     {
       blockIdx.x = b;
-      if (s.dyn_smem) memset(s.dyn_smem, 0xA5, s.dyn_cap);  // poison: shared memory is not zero-initialised
+      memset(s.dyn_smem, 0xFF, smem);  // poison (NaN as double): shared memory is not zero-initialised
+      memset(s.dyn_smem + smem, 0x5A, CANARY);
       run_block(block, [&]() { f(args...); });
+      for (size_t i = 0; i < CANARY; i++)
+        if ((unsigned char)s.dyn_smem[smem + i] != 0x5A)
+        {
+          fprintf(stderr, "emu: write past the %zu bytes of dynamic shared memory (block %u)\n", smem, b);
+          abort();
+        }
     }
   }
 };
@@ -110,13 +116,34 @@ using std::min;
 
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-template <typename T> inline cudaError_t cudaMalloc(T **p, size_t bytes)
+// device allocations: [size header 256 B | payload (poisoned) | canary 256 B]; cudaFree aborts on a damaged canary
+inline cudaError_t emu_malloc(void **p, size_t bytes)
 {
-  *p = (T *)aligned_alloc(256, (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255);
-  if (*p) memset((void *)*p, 0xCD, bytes);  // device memory is not zero-initialised
-  return *p ? cudaSuccess : 2;
+  const size_t pay = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+  char *raw = (char *)aligned_alloc(256, pay + 512);
+  if (!raw) return 2;
+  *(size_t *)raw = bytes;
+  memset(raw + 256, 0xCD, pay);  // device memory is not zero-initialised
+  memset(raw + 256 + bytes, 0x5A, pay - bytes + 256);
+  *p = raw + 256;
+  return cudaSuccess;
 }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+template <typename T> inline cudaError_t cudaMalloc(T **p, size_t bytes) { return emu_malloc((void **)p, bytes); }
+inline cudaError_t cudaFree(void *p)
+{
+  if (!p) return cudaSuccess;
+  char *raw = (char *)p - 256;
+  const size_t bytes = *(size_t *)raw;
+  const size_t pay = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+  for (size_t i = bytes; i < pay + 256; i++)
+    if ((unsigned char)raw[256 + i] != 0x5A)
+    {
+      fprintf(stderr, "emu: write past a device allocation of %zu bytes (offset %zu)\n", bytes, i);
+      abort();
+    }
+  free(raw);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }

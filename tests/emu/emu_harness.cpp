@@ -33,7 +33,8 @@ int run_matvec(DA &, const dkt_op *, const double *, double *, double, unsigned)
 template <typename T>
 static T *dup(const T *src, size_t n)
 {
-  T *p = (T *)malloc(std::max<size_t>(n, 1) * sizeof(T));
+  T *p = nullptr;
+  cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
   if (src && n) memcpy(p, src, n * sizeof(T));
   return p;
 }
@@ -82,11 +83,11 @@ extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint6
     else  // the three phases of run_matvec_dist, without the exchanges
       for (int ph = 0; ph < 3 && rc == DKT_OK; ph++) rc = run_matvec_chunked(da, &op, din, dout, scale, flags, 1u << ph, ph == 0);
     memcpy(out, dout, nNodes * sizeof(double));
-    free(din);
-    free(dout);
+    cudaFree(din);
+    cudaFree(dout);
   }
   free_chunks(da);
-  free(da.d_e2n); free(da.d_pnode); free(da.d_mv_xyz); free(da.d_mv_lev); free(da.d_mv_src); free(da.d_node_isbdy);
+  cudaFree(da.d_e2n); cudaFree(da.d_pnode); cudaFree(da.d_mv_xyz); cudaFree(da.d_mv_lev); cudaFree(da.d_mv_src); cudaFree(da.d_node_isbdy);
   return rc;
 }
 extern "C" void emu_set_order(int order) { emu::state().order = order; }
