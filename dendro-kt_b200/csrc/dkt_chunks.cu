@@ -108,8 +108,13 @@ constexpr int GRP_TPB = 128;                // threads (= units per chunk at mos
 #ifndef DKT_HANG_MINB
 #define DKT_HANG_MINB 4
 #endif
-#ifndef DKT_GRP_MINB
-#define DKT_GRP_MINB 2   // resident CTAs per SM the group kernels are compiled for
+// resident CTAs per SM the group kernels are compiled for.  ptxas, 4-D quads: 2 -> 212 (regular) / 255 (hanging)
+// registers, no spills; 3 -> 168 registers, 64 B / ~0.9 KB of spills
+#ifndef DKT_GRP_MINB_REG
+#define DKT_GRP_MINB_REG 2
+#endif
+#ifndef DKT_GRP_MINB_HANG
+#define DKT_GRP_MINB_HANG 2
 #endif
 int rows_per_chunk(int N)
 {
@@ -1435,7 +1440,7 @@ __device__ __forceinline__ void grp_expand(const double *src, double *dst)
 }
 
 template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
-__global__ void __launch_bounds__(TPB, DKT_GRP_MINB) k_mvg(const __grid_constant__ Mv3Params<DIM, 1> p)
+__global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_REG) k_mvg(const __grid_constant__ Mv3Params<DIM, 1> p)
 {
   using GP = Grp<DIM, G>;
   constexpr int N = GP::N, LP = GP::LP, NC = GP::NC;
