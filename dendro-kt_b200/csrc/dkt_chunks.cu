@@ -110,6 +110,9 @@ constexpr int GRP_TPB = 128;                // threads (= units per chunk at mos
 #endif
 // resident CTAs per SM the group kernels are compiled for.  ptxas, 4-D quads: 2 -> 212 (regular) / 255 (hanging)
 // registers, no spills; 3 -> 168 registers, 64 B / ~0.9 KB of spills
+#ifndef DKT_GRP_RSHARE
+#define DKT_GRP_RSHARE 1  // regular groups: shared butterflies along the XOR-permuted dimensions (see k_mvg)
+#endif
 #ifndef DKT_GRP_MINB_REG
 #define DKT_GRP_MINB_REG 2
 #endif
@@ -1439,6 +1442,43 @@ __device__ __forceinline__ void grp_expand(const double *src, double *dst)
     }
 }
 
+// butterflies of the strides LO, 2 LO, .. < HI
+template <int N, int LO, int HI>
+__device__ __forceinline__ void wht_range(double *v)
+{
+#pragma unroll
+  for (int s = LO; s < HI; s <<= 1)
+  {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      if (i & s) continue;
+      const double a = v[i], b = v[i + s];
+      v[i] = a + b;
+      v[i + s] = a - b;
+    }
+  }
+}
+// Walsh-Hadamard butterflies along the XOR-permuted dimensions (>= G) of a group lattice, index xg + 3^G * sR
+template <int DIM, int G>
+__device__ __forceinline__ void grp_wht_lattice(double *v)
+{
+  using GP = Grp<DIM, G>;
+#pragma unroll
+  for (int k = 0; k < DIM - G; k++)
+  {
+    const int st = GP::L3 << k;
+#pragma unroll
+    for (int l = 0; l < GP::LP; l++)
+    {
+      if ((l / st) & 1) continue;
+      const double a = v[l], b = v[l + st];
+      v[l] = a + b;
+      v[l + st] = a - b;
+    }
+  }
+}
+
 template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
 __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_REG) k_mvg(const __grid_constant__ Mv3Params<DIM, 1> p)
 {
@@ -1551,6 +1591,12 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
         {
 #pragma unroll
           for (int l = 0; l < LP; l++) v[l] = un[GRK(l)];
+          // Walsh-Hadamard form: the butterflies along the XOR-permuted dimensions are the same for every child of the
+          // group, so they run ONCE on the lattice (forward here, backward on the summed output); the children then only
+          // transform along the grouped dimensions.  (H D H commutes with the XOR permutation: its signs in the
+          // frequency domain cancel around the diagonal D.)
+          constexpr bool RSHARE = (OPKIND == OP_HADAMARD) && (DKT_GRP_RSHARE != 0) && (G < DIM);
+          if (RSHARE) grp_wht_lattice<DIM, G>(v);
 #pragma unroll
           for (int cG = 0; cG < NC; cG++)
           {
@@ -1559,10 +1605,10 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
             for (int r = 0; r < N; r++) e[r] = v[GP::lat(cG, r)];
             if (OPKIND == OP_HADAMARD)
             {
-              wht<N>(e);
+              wht_range<N, 1, (RSHARE ? NC : N)>(e);
 #pragma unroll
               for (int i = 0; i < N; i++) e[i] *= p.K[i] * s;
-              wht<N>(e);
+              wht_range<N, 1, (RSHARE ? NC : N)>(e);
             }
 #pragma unroll
             for (int r = 0; r < N; r++)
@@ -1571,6 +1617,7 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
               else o[GP::lat(cG, r)] += e[r];
             }
           }
+          if (RSHARE) grp_wht_lattice<DIM, G>(o);
 #pragma unroll
           for (int l = 0; l < LP; l++) X[GPS(l)] = o[l];
         }
