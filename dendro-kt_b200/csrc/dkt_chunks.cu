@@ -492,6 +492,15 @@ void free_chunks(DA &da)
     for (void *p : cs.owned) cudaFree(p);
   }
   da.sets.clear();
+  if (da.ev_fork) cudaEventDestroy(da.ev_fork);
+  da.ev_fork = nullptr;
+  for (int a = 0; a < DA::MAX_AUX; a++)
+  {
+    if (da.aux[a]) cudaStreamDestroy(da.aux[a]);
+    if (da.ev_join[a]) cudaEventDestroy(da.ev_join[a]);
+    da.aux[a] = nullptr;
+    da.ev_join[a] = nullptr;
+  }
 }
 
 __global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_t n, int dim, int max_depth, uint8_t *child)
@@ -938,6 +947,17 @@ int build_chunks(DA &da)
   int dev = 0;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&da.numSMs, cudaDevAttrMultiProcessorCount, dev));
+  da.mvStreams = 1;
+  if (const char *e = getenv("DKT_MV_STREAMS")) da.mvStreams = std::max(1, std::min(atoi(e), DA::MAX_AUX + 1));
+  if (da.mvStreams > 1 && !da.ev_fork)
+  {
+    CK(cudaEventCreateWithFlags(&da.ev_fork, cudaEventDisableTiming));
+    for (int a = 0; a < da.mvStreams - 1; a++)
+    {
+      CK(cudaStreamCreateWithFlags(&da.aux[a], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&da.ev_join[a], cudaEventDisableTiming));
+    }
+  }
   return rc;
 }
 
@@ -1384,7 +1404,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
   int sms = da.numSMs;
   if (da.phased && cs.phase != 1) sms = std::max(1, da.numSMs - da.commSMs);
   const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * sms));
-  DKT_LAUNCH(kern, grid, TPB, smem, da.stream)(p);
+  DKT_LAUNCH(kern, grid, TPB, smem, da.cur ? da.cur : da.stream)(p);
   g_launches++;
   return DKT_OK;
 }
@@ -1770,7 +1790,7 @@ static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TPB, smem));
   if (perSM < 1) { set_error("group kernel does not fit on an SM"); return DKT_ERR_CUDA; }
   const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * da.numSMs));
-  DKT_LAUNCH(kern, grid, TPB, smem, da.stream)(p);
+  DKT_LAUNCH(kern, grid, TPB, smem, da.cur ? da.cur : da.stream)(p);
   g_launches++;
   return DKT_OK;
 }
@@ -1806,10 +1826,27 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
   constexpr int TPB_H = (N == 27) ? 96 : DKT_ROWS / 2;
   constexpr bool CAN_EXIP = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
   const bool exip = CAN_EXIP && p.exact_ip;
+  // DKT_MV_STREAMS=n (opt-in): the sets of one call are independent (nodes shared between sets are accumulated with
+  // RED), so they may run side by side on n streams - small sets then fill the tails of the big ones
+  const int ns = std::min(da.mvStreams, DA::MAX_AUX + 1);
+  int k = 0, used = 0;
   for (const ChunkSet &cs : da.sets)
   {
     if (!cs.nChunks || !((phaseMask >> cs.phase) & 1u)) continue;
     int rc = DKT_OK;
+    da.cur = nullptr;
+    if (ns > 1)
+    {
+      if (k == 0) CK(cudaEventRecord(da.ev_fork, da.stream));
+      const int a = k % ns;
+      if (a > 0)
+      {
+        da.cur = da.aux[a - 1];
+        if (!((used >> a) & 1)) CK(cudaStreamWaitEvent(da.cur, da.ev_fork, 0));
+        used |= 1 << a;
+      }
+      k++;
+    }
     if (cs.kind == 1) rc = launch_group<DIM, ORDER, OPKIND, DIRI>(da, cs, p);
     else if (cs.rows == 1)
     {
@@ -1822,8 +1859,15 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
       else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, cs, p);
     }
     else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, cs, p);
+    da.cur = nullptr;
     if (rc) return rc;
   }
+  for (int a = 1; a < ns; a++)
+    if ((used >> a) & 1)
+    {
+      CK(cudaEventRecord(da.ev_join[a - 1], da.aux[a - 1]));
+      CK(cudaStreamWaitEvent(da.stream, da.ev_join[a - 1], 0));
+    }
   CK(cudaGetLastError());
   return DKT_OK;
 }

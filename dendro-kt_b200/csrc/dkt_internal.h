@@ -102,7 +102,13 @@ struct DA
   uint64_t nRegInterior = 0, nHangInterior = 0;
   bool phased = false;
   int commSMs = 0;                 // SMs left to the NCCL kernels during the interior phases
-  int groups = 0;                  // DKT_GROUPS=g at construction: sibling-group sets in use (single rank, order 1)
+  int groups = 0;                  // DKT_GROUPS=g at construction: sibling-group sets in use (order 1)
+  // DKT_MV_STREAMS=n (opt-in): the chunk sets of one matvec call run on n streams (dkt_chunks.cu launch_mv3)
+  static constexpr int MAX_AUX = 3;
+  int mvStreams = 1;
+  cudaStream_t aux[MAX_AUX] = {nullptr, nullptr, nullptr};
+  cudaStream_t cur = nullptr;      // stream of the set being launched (nullptr: `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr};
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)

@@ -12,6 +12,12 @@ for g in 0 2 3; do
   timeout 600 python bench.py --groups $g --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g$g.json 2> $out/bench_g$g.err
   echo "bench groups=$g rc=$?" | tee -a $out/summary.txt
 done
+# the sets of one matvec on several streams (DKT_MV_STREAMS): small sets fill the tails of the big ones
+for st in 2 4; do
+  DKT_MV_STREAMS=$st timeout 600 python bench.py --groups 2 --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g2_s$st.json 2> $out/bench_g2_s$st.err
+  echo "bench groups=2 streams=$st rc=$?" | tee -a $out/summary.txt
+done
+DKT_MV_STREAMS=2 timeout 600 python bench.py --groups 0 --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g0_s2.json 2> $out/bench_g0_s2.err
 # launch list (per-kernel device time) and one full capture of the group kernels
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_g2.csv \
   python bench.py --groups 2 --steps 3 --warmup 2 --no-experimental --no-cpu-baseline > $out/ncu_launches.log 2>&1
@@ -19,6 +25,15 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_m
   python bench.py --groups 2 --steps 2 --warmup 1 --no-experimental --no-cpu-baseline > $out/ncu_full.log 2>&1
 python tools/ncu_summary.py $out/mvg_g2.ncu-rep k_mvg > $out/ncu_mvg_g2.txt 2>&1
 tail -n 3 $out/pytest_groups.log
+for f in $out/bench_g*_s*.json; do python - <<PY
+import json
+try:
+    d = json.loads(open("$f").read().strip().splitlines()[-1])
+    print("$f", "ms", round(d["ms_per_step"], 4), "DOF/s %.3e" % d["value"], "frac", round(d["roofline"]["frac"], 4))
+except Exception as e:
+    print("$f", "no result", e)
+PY
+done
 for g in 0 2 3; do python - <<PY
 import json
 try:
