@@ -1743,17 +1743,39 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
     __syncthreads();  // B: X complete
     // ---- T4: own nodes of this chunk
     {
+      // four nodes per thread at a time: independent accumulation chains, one jd[j] load for the four.  Nodes are
+      // ranked by run length (descending), so the first of the four has the longest run.
       const uint2 *rec = recb + buf * p.ncap;
-      for (int n = tid; n < nlocC; n += TPB)
+      for (int base = tid; base < nlocC; base += 4 * TPB)
       {
-        const uint2 r = rec[n];
-        const int len = r.y & META_LEN;
-        if (len == 0) continue;  // only read by this chunk
-        double acc = X[n];       // jd[0] == 0
-        for (int j = 1; j < len; j++) acc += X[jd[j] + n];
-        if (DIRI && (r.y & META_BDY)) continue;
-        if (r.y & META_SHARED) atomicAdd(p.out + r.x, acc);
-        else p.out[r.x] = acc;
+        uint2 r[4];
+        int len[4];
+        double acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          const int n = base + i * TPB;
+          r[i] = make_uint2(0u, 0u);
+          if (n < nlocC) r[i] = rec[n];
+          len[i] = (int)(r[i].y & META_LEN);
+          acc[i] = len[i] ? X[n] : 0.0;  // jd[0] == 0
+        }
+        const int lmax = len[0];
+        for (int j = 1; j < lmax; j++)
+        {
+          const int off = jd[j] + base;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (j < len[i]) acc[i] += X[off + i * TPB];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          if (len[i] == 0) continue;  // beyond the chunk's nodes, or only read by this chunk
+          if (DIRI && (r[i].y & META_BDY)) continue;
+          if (r[i].y & META_SHARED) atomicAdd(p.out + r[i].x, acc[i]);
+          else p.out[r[i].x] = acc[i];
+        }
       }
     }
     if (!hasN) break;
