@@ -1439,6 +1439,13 @@ struct Grp
     }
     return xg + L3 * (r >> G);
   }
+  // the lattice slots of child cG as a bit mask
+  __host__ __device__ static constexpr unsigned long long child_mask(int cG)
+  {
+    unsigned long long m = 0;
+    for (int r = 0; r < N; r++) m |= 1ull << lat(cG, r);
+    return m;
+  }
   // child cG is the first (smallest) child touching the lattice point of its rank r
   __host__ __device__ static constexpr bool first(int cG, int r) { return ((cG & ~r) & (NC - 1)) == 0; }
 };
@@ -1680,6 +1687,8 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
           }
           double ta[N];
 #pragma unroll
+          for (int q = 0; q < N; q++) ta[q] = 0.0;
+#pragma unroll
           for (int cG = 0; cG < NC; cG++)
           {
             double e[N];
@@ -1697,8 +1706,13 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
             {
               if (GP::first(cG, r)) o[GP::lat(cG, r)] = e[r];
               else o[GP::lat(cG, r)] += e[r];
-              if ((fm >> GP::lat(cG, r)) & 1ull) e[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
             }
+            // a child without hanging nodes sends nothing to the parent nodes.  Neighbouring groups hang on the same
+            // coarse face, so the branch is mostly warp-uniform.
+            if ((~fm & GP::child_mask(cG)) == 0ull) continue;
+#pragma unroll
+            for (int r = 0; r < N; r++)
+              if ((fm >> GP::lat(cG, r)) & 1ull) e[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
             // transposed interpolation of this child: A0^T along permuted dimensions and grouped ones with bit 0, A1^T otherwise
 #pragma unroll
             for (int d = 0; d < DIM; d++)
@@ -1727,9 +1741,7 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
 #pragma unroll
             for (int q = 0; q < N; q++)
             {
-              const double t = ((fm >> GP::lat(cG, q)) & 1ull) ? 0.0 : e[q];
-              if (cG == 0) ta[q] = t;
-              else ta[q] += t;
+              ta[q] += ((fm >> GP::lat(cG, q)) & 1ull) ? 0.0 : e[q];
             }
           }
 #pragma unroll
