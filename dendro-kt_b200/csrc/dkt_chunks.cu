@@ -86,7 +86,7 @@ namespace dkt
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;                       // per-element sets: 4096 slots per chunk
-constexpr int SORT_ITEMS_GRP = 18;                   // sibling-group sets: 4608 slots per chunk (128 quads of 36)
+constexpr int SORT_ITEMS_GRP = 20;                   // sibling-group sets: 5120 slots per chunk (128 quads of 36, 96 hanging quads of 52)
 constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;
 constexpr int SLOT_CAP_GRP = SORT_THREADS * SORT_ITEMS_GRP;
 constexpr int MAX_LEN = 511;                         // run length of a node inside a chunk (9 bits)
@@ -96,6 +96,15 @@ constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
 constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
 constexpr int GRP_TPB = 128;                // threads (= units per chunk at most) of the group kernels
+// units per chunk of a group set with `spu` slots per unit: what the block sort holds, rounded down to whole warps
+// when that costs at most an eighth; threads of its kernel: the next multiple of 32
+constexpr int grp_upc(int spu)
+{
+  const int u = (SORT_THREADS * SORT_ITEMS_GRP / spu) < GRP_TPB ? (SORT_THREADS * SORT_ITEMS_GRP / spu) : GRP_TPB;
+  const int r = u & ~31;
+  return (r > 0 && (u - r) * 8 <= u) ? r : u;
+}
+constexpr int grp_tpb(int spu) { return (grp_upc(spu) + 31) & ~31; }
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
@@ -730,7 +739,7 @@ static int add_group_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *
   const int LP = L3 << (da.dim - g);
   cs.rows = hang ? 2 : 1; cs.phase = phase; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
   cs.spu = (LP + (hang ? da.N : 0) + 1) & ~1;
-  cs.elemsPerChunk = std::min(SLOT_CAP_GRP / cs.spu, GRP_TPB);
+  cs.elemsPerChunk = grp_upc(cs.spu);
   uint32_t *U = nullptr;
   uint8_t *lev_g = nullptr;
   unsigned long long *fm = nullptr;
@@ -1804,11 +1813,12 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
 #undef GPS
 }
 
-template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
+template <int DIM, int G, int OPKIND, bool DIRI, bool HANG>
 static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
 {
   using GP = Grp<DIM, G>;
   constexpr int SPU = (GP::LP + (HANG ? GP::N : 0) + 1) & ~1;
+  constexpr int TPB = grp_tpb(SPU);
   if (cs.spu != SPU || (int)cs.elemsPerChunk > TPB) { set_error("internal: group set does not match its kernel"); return DKT_ERR_INVALID; }
   p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint2 *)cs.d_rec; p.jd = cs.d_jd;
   p.node_off = cs.d_node_off; p.lev = cs.lev; p.fmask64 = cs.fmask64;
@@ -1835,17 +1845,17 @@ static int launch_group(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
   if constexpr (ORDER == 1 && (OPKIND == DKT_OP_IDENTITY || OPKIND == OP_HADAMARD))
   {
     const bool hang = cs.rows == 2;
-#define GRP_CASE(D, GG, TR, TH)                                                              \
+#define GRP_CASE(D, GG)                                                                      \
   if constexpr (DIM == D)                                                                    \
   {                                                                                          \
     if (cs.g == GG)                                                                          \
-      return hang ? launch_group_one<DIM, GG, OPKIND, DIRI, true, TH>(da, cs, p)             \
-                  : launch_group_one<DIM, GG, OPKIND, DIRI, false, TR>(da, cs, p);           \
+      return hang ? launch_group_one<DIM, GG, OPKIND, DIRI, true>(da, cs, p)                 \
+                  : launch_group_one<DIM, GG, OPKIND, DIRI, false>(da, cs, p);               \
   }
-    GRP_CASE(4, 2, 128, 96)
-    GRP_CASE(4, 3, 96, 96)
-    GRP_CASE(3, 3, 128, 128)
-    GRP_CASE(2, 2, 128, 128)
+    GRP_CASE(4, 2)
+    GRP_CASE(4, 3)
+    GRP_CASE(3, 3)
+    GRP_CASE(2, 2)
 #undef GRP_CASE
   }
   set_error("internal: no sibling-group kernel for this (dim, g, operator)");
