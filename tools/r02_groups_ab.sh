@@ -8,6 +8,14 @@ mkdir -p $out
 python __graft_entry__.py > $out/build.log 2>&1
 DKT_TEST_GROUPS=1 timeout 900 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu > $out/pytest_groups.log 2>&1
 echo "pytest groups rc=$?" | tee -a $out/summary.txt
+# memory and shared-memory race checks of the group kernels on one small 4-D tree (the CPU emulation cannot see
+# real races or misaligned accesses)
+DKT_TEST_GROUPS=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu \
+  -k "ex3-d4-p1-morton-3" > $out/sanitizer_memcheck.log 2>&1
+echo "memcheck rc=$?" | tee -a $out/summary.txt
+DKT_TEST_GROUPS=1 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu \
+  -k "ex3-d4-p1-morton-3" > $out/sanitizer_racecheck.log 2>&1
+echo "racecheck rc=$?" | tee -a $out/summary.txt
 for g in 0 2 3; do
   timeout 600 python bench.py --groups $g --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g$g.json 2> $out/bench_g$g.err
   echo "bench groups=$g rc=$?" | tee -a $out/summary.txt
