@@ -195,7 +195,7 @@ def groups_probe(args):
     print(json.dumps(out))
 
 
-def run_groups_probe_subprocess(args, g=2, timeout=180):
+def run_groups_probe_subprocess(args, g="2", timeout=180):
     """The experimental leg of the default run: never raises, never touches the headline numbers."""
     cmd = [sys.executable, os.path.abspath(__file__), "--groups-probe", str(g), "--steps", str(min(args.steps, 10)), "--warmup", "3",
            "--level", str(args.level), "--per-gpu-elems", str(args.per_gpu_elems)]
@@ -219,7 +219,7 @@ def run_gpu(args):
     import torch
     import dkt
     from dkt import operators
-    if args.groups:
+    if args.groups != "0":
         os.environ["DKT_GROUPS"] = str(args.groups)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -351,12 +351,12 @@ def run_gpu(args):
                        "n_hanging_elem": int(n_hang_total), "n_ghost_nodes": int(n_ghost_total), "tree_class": da.tree_class,
                        "partition": "SFC-contiguous element ranges, one per GPU; NCCL send/recv ghost exchange" if world > 1 else "single GPU",
                        "cache": "working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (alg_total / world / 1e6),
-                       "groups": int(args.groups),
+                       "groups": args.groups,
                        "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3), "chunks_rank0": da.chunk_info()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # ncu dram__bytes_read+write of the step's kernels on the default workload (profiles/README.md);
                          # None for other workloads
-                         "traffic": 1.78e9 if (world == 1 and level == 9 and args.per_gpu_elems == 1.2e7 and not args.groups) else None,
+                         "traffic": 1.78e9 if (world == 1 and level == 9 and args.per_gpu_elems == 1.2e7 and args.groups == "0") else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                          "alg_bytes_per_step_per_gpu": alg_total / world,
                          "kernel": "whole matvec step per GPU (memset + chunked regular + hanging kernels" +
@@ -374,10 +374,10 @@ def run_gpu(args):
                 line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
             except Exception as e:  # the bench line must survive a missing oracle
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
-        if args.experimental and world == 1 and not args.groups:
+        if args.experimental and world == 1 and args.groups == "0":
             # opt-in sibling-group tables (DKT_GROUPS, validated against the oracle in the CPU emulation, tests/test_emu_chunks.py):
             # timed in a separate process AFTER the headline measurement; informational only
-            line["experimental_groups"] = [run_groups_probe_subprocess(args, g=2, timeout=150), run_groups_probe_subprocess(args, g=3, timeout=150)]
+            line["experimental_groups"] = [run_groups_probe_subprocess(args, g=g, timeout=150) for g in ("2", "2,1", "3,2")]
         print(json.dumps(line))
     da.close()
     if dist is not None:
@@ -394,8 +394,8 @@ def main():
     ap.add_argument("--per-gpu-elems", type=float, default=1.2e7, help="weak scaling: target elements per GPU (level 9)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: replicas (0 = one per core, at most 64)")
-    ap.add_argument("--groups", type=int, default=0, help="build the DA with sibling-group tables (DKT_GROUPS=g; opt-in)")
-    ap.add_argument("--groups-probe", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--groups", default="0", help="build the DA with sibling-group tables (DKT_GROUPS=g or gR,gH; opt-in)")
+    ap.add_argument("--groups-probe", default="", help=argparse.SUPPRESS)
     ap.add_argument("--no-experimental", dest="experimental", action="store_false",
                     help="skip the separate-process timing of the opt-in sibling-group tables")
     args = ap.parse_args()

@@ -588,8 +588,10 @@ __device__ __forceinline__ int elem_class(uint64_t e, uint64_t nReg, uint64_t nR
   const int bdy = phased && (hang ? (e - nReg >= nHangInt) : (e >= nRegInt));
   return (hang << 1) | bdy;
 }
-__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, uint64_t nReg, uint64_t nRegInt, uint64_t nHangInt,
-                              int phased, uint8_t *cls)
+// mode 0: plain.  mode 1 (groups of 2^g with smaller hanging groups to follow): hanging groups get class 255.
+// mode 2 (the smaller groups, gOuter > g): groups inside a REGULAR outer group get class 255 - that one has them.
+__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, int gOuter, int mode, uint64_t nReg, uint64_t nRegInt,
+                              uint64_t nHangInt, int phased, uint8_t *cls)
 {
   uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (u >= nGroups) return;
@@ -598,6 +600,14 @@ __global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, in
   const int cR = (int)(u % NR);
   int c = 0;
   for (int cG = 0; cG < NC; cG++) c |= elem_class(mem[(f << dim) + ((cR << g) | cG)], nReg, nRegInt, nHangInt, phased);
+  if (mode == 1 && (c & 2)) c = 255;
+  if (mode == 2)
+  {
+    const int cRo = cR >> (gOuter - g);
+    bool outerHang = false;
+    for (int cG = 0; cG < (1 << gOuter); cG++) outerHang |= mem[(f << dim) + ((cRo << gOuter) | cG)] >= nReg;
+    if (!outerHang) c = 255;
+  }
   cls[u] = (uint8_t)c;
 }
 // the elements outside complete families: class as above, 255 for family members
@@ -790,13 +800,22 @@ static int add_single_set(DA &da, std::vector<PendingSet> &pend, const uint32_t 
 }
 
 // DKT_GROUPS=g: group the leaves of complete sibling families (see the file header).  0 / unset: off.
-static int groups_requested(const DA &da)
+// "g" or "gR,gH" (gH <= gR): regular groups of 2^gR leaves; groups of that size with a hanging member are split into
+// groups of 2^gH leaves, which are regular or hanging in their turn (smaller hanging groups need fewer registers).
+static bool group_kernel_exists(int dim, int g)
 {
+  return (dim == 4 && g >= 1 && g <= 3) || (dim == 3 && (g == 2 || g == 3)) || (dim == 2 && g == 2);
+}
+static int groups_requested(const DA &da, int &gH)
+{
+  gH = 0;
   const char *e = getenv("DKT_GROUPS");
   if (!e) return 0;
   const int g = atoi(e);
-  if (g <= 0 || da.order != 1 || g > da.dim) return 0;
-  if (!((da.dim == 4 && (g == 2 || g == 3)) || (da.dim == 3 && g == 3) || (da.dim == 2 && g == 2))) return 0;
+  gH = g;
+  if (const char *c = strchr(e, ',')) gH = atoi(c + 1);
+  if (g <= 0 || da.order != 1 || gH <= 0 || gH > g) return 0;
+  if (!group_kernel_exists(da.dim, g) || !group_kernel_exists(da.dim, gH)) return 0;
   return g;
 }
 
@@ -817,7 +836,8 @@ int build_chunks(DA &da)
   }
   std::vector<PendingSet> pend;
   int rc = DKT_OK;
-  const int g = groups_requested(da);
+  int gHang = 0;
+  const int g = groups_requested(da, gHang);
   da.groups = g;
   if (!g)
   {
@@ -847,7 +867,7 @@ int build_chunks(DA &da)
   else
   {
     const uint64_t n = da.nMv;
-    const int nch = 1 << da.dim, NC = 1 << g, NR = 1 << (da.dim - g);
+    const int nch = 1 << da.dim;
     const int phased = da.phased ? 1 : 0;
     uint32_t *inv = nullptr, *mem = nullptr;
     uint64_t *flag = nullptr, *pos = nullptr;
@@ -869,7 +889,7 @@ int build_chunks(DA &da)
     g_launches++;
     std::vector<uint32_t *> lists;  // freed after the unit slot tables are built
     // interior units run in two halves around the boundary ones (see run_matvec_dist); unpartitioned: one set
-    auto add_sets = [&](const uint32_t *list, uint64_t cnt, int width, int c, bool group) -> int {
+    auto add_sets = [&](const uint32_t *list, uint64_t cnt, int width, int c, int gsz) -> int {
       const int hang = (c >> 1) & 1, bdy = c & 1;
       struct Sub { uint64_t a, b; int phase; };
       std::vector<Sub> subs;
@@ -878,23 +898,28 @@ int build_chunks(DA &da)
       else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
       for (const Sub &s : subs)
       {
-        const int r = group ? add_group_set(da, pend, list + s.a * width, s.b - s.a, g, hang, s.phase)
-                            : add_single_set(da, pend, list + s.a, s.b - s.a, hang, s.phase);
+        const int r = gsz ? add_group_set(da, pend, list + s.a * width, s.b - s.a, gsz, hang, s.phase)
+                          : add_single_set(da, pend, list + s.a, s.b - s.a, hang, s.phase);
         if (r) return r;
       }
       return DKT_OK;
     };
-    // groups by class: regular / hanging x interior / boundary
-    const uint64_t nGroups = nFam * NR;
-    if (nGroups)
+    // groups by class: regular / hanging x interior / boundary; with DKT_GROUPS=gR,gH a second pass makes the
+    // smaller groups out of the size-2^gR groups that have a hanging member
+    for (int pass = 0; pass < (gHang < g ? 2 : 1) && rc == DKT_OK; pass++)
     {
+      const int gp = pass == 0 ? g : gHang;
+      const int mode = gHang < g ? pass + 1 : 0;
+      const int NCp = 1 << gp;
+      const uint64_t nGroups = nFam << (da.dim - gp);
+      if (!nGroups) continue;
       uint64_t *gflag = nullptr, *gpos = nullptr;
       uint8_t *gcls = nullptr;
       CK(cudaMalloc((void **)&gflag, (nGroups + 1) * sizeof(uint64_t)));
       CK(cudaMalloc((void **)&gpos, (nGroups + 1) * sizeof(uint64_t)));
       CK(cudaMalloc((void **)&gcls, nGroups));
-      DKT_LAUNCH(k_group_class, nblk(nGroups), 256, 0, da.stream)(mem, nGroups, da.dim, g, da.nReg, da.nRegInterior, da.nHangInterior, phased,
-                                                                  gcls);
+      DKT_LAUNCH(k_group_class, nblk(nGroups), 256, 0, da.stream)(mem, nGroups, da.dim, gp, g, mode, da.nReg, da.nRegInterior,
+                                                                  da.nHangInterior, phased, gcls);
       g_launches++;
       for (int c = 0; c < 4 && rc == DKT_OK; c++)
       {
@@ -904,11 +929,11 @@ int build_chunks(DA &da)
         rc = scan_total(da, gflag, gpos, nGroups, cnt);
         if (rc || !cnt) continue;
         uint32_t *list = nullptr;
-        CK(cudaMalloc((void **)&list, cnt * NC * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&list, cnt * NCp * sizeof(uint32_t)));
         lists.push_back(list);
-        DKT_LAUNCH(k_group_list, nblk(nGroups), 256, 0, da.stream)(mem, gflag, gpos, nGroups, da.dim, g, list);
+        DKT_LAUNCH(k_group_list, nblk(nGroups), 256, 0, da.stream)(mem, gflag, gpos, nGroups, da.dim, gp, list);
         g_launches++;
-        rc = add_sets(list, cnt, NC, c, true);
+        rc = add_sets(list, cnt, NCp, c, gp);
       }
       CK(cudaStreamSynchronize(da.stream));
       cudaFree(gflag); cudaFree(gpos); cudaFree(gcls);
@@ -928,7 +953,7 @@ int build_chunks(DA &da)
       lists.push_back(list);
       DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
       g_launches++;
-      rc = add_sets(list, cnt, 1, c, false);
+      rc = add_sets(list, cnt, 1, c, 0);
     }
     CK(cudaStreamSynchronize(da.stream));
     for (uint32_t *l : lists) cudaFree(l);
@@ -1852,8 +1877,10 @@ static int launch_group(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
       return hang ? launch_group_one<DIM, GG, OPKIND, DIRI, true>(da, cs, p)                 \
                   : launch_group_one<DIM, GG, OPKIND, DIRI, false>(da, cs, p);               \
   }
+    GRP_CASE(4, 1)
     GRP_CASE(4, 2)
     GRP_CASE(4, 3)
+    GRP_CASE(3, 2)
     GRP_CASE(3, 3)
     GRP_CASE(2, 2)
 #undef GRP_CASE

@@ -101,3 +101,27 @@ def test_emulated_phased_sets(name, groups):
     assert {s[8] for s in sets} == {0, 1, 2}
     units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
     assert units == len(t.mv_lev)
+
+
+@pytest.mark.parametrize("name,groups", [("ball-d4-p1-morton-5", "2,1"), ("ex3-d4-p1-morton-3", "3,2"), ("ex3-d4-p1-morton-3", "3,1"),
+                                         ("gauss-d4-p1-morton", "2,1"), ("ex1-d4-p1-morton-3", "1"), ("ball-d3-p1-morton-6", "3,2"),
+                                         ("ex3-d3-p1-hilbert-3", "2"), ("gauss-d3-p1-morton", "3,2")])
+def test_emulated_two_level_groups(name, groups):
+    """DKT_GROUPS=gR,gH: regular groups of 2^gR leaves, the others split into groups of 2^gH"""
+    case, g, t = _tables(name)
+    dim, md = case["dim"], case["max_depth"]
+    n = len(g["node_lev"])
+    v, sets = emu_chunks.matvec(t, np.ones(n), md, ip0=g["ip0"], ip1=g["ip1"], groups=groups)
+    assert rel(v, g["v_id"]) <= TOL
+    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
+    assert units == len(t.mv_lev)
+    gs = [int(x) for x in groups.split(",")]
+    assert all(s[2] in gs for s in sets if s[0] == 1)
+    if len(gs) == 2:
+        assert not any(s[0] == 1 and s[1] == 2 and s[2] == gs[0] for s in sets), "hanging groups must have the smaller size"
+    K = flat.laplace_kref(dim, 1)
+    u = cases.input_vector(n)
+    ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
+    v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True, groups=groups,
+                             order=2, phased_seed=(5 if len(t.mv_lev) < 50000 else None))
+    assert rel(v, ref) <= TOL

@@ -16,7 +16,7 @@ echo "memcheck rc=$?" | tee -a $out/summary.txt
 DKT_TEST_GROUPS=1 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu \
   -k "ex3-d4-p1-morton-3" > $out/sanitizer_racecheck.log 2>&1
 echo "racecheck rc=$?" | tee -a $out/summary.txt
-for g in 0 2 3; do
+for g in 0 2 3 2,1 3,2; do
   timeout 600 python bench.py --groups $g --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g$g.json 2> $out/bench_g$g.err
   echo "bench groups=$g rc=$?" | tee -a $out/summary.txt
 done
@@ -42,7 +42,7 @@ except Exception as e:
     print("$f", "no result", e)
 PY
 done
-for g in 0 2 3; do python - <<PY
+for g in 0 2 3 2,1 3,2; do python - <<PY
 import json
 try:
     d = json.loads(open("$out/bench_g$g.json").read().strip().splitlines()[-1])
