@@ -12,7 +12,7 @@ from test_oracle import load_case
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DKT_TEST_GROUPS") != "1", reason="opt-in: DKT_TEST_GROUPS=1")]
 TOL = 1e-12
-GROUP_G = {2: (2,), 3: (3,), 4: (2, 3)}
+GROUP_G = {2: ("2",), 3: ("3", "3,2"), 4: ("2", "3", "2,1", "3,2")}
 
 
 @pytest.fixture
@@ -58,8 +58,8 @@ def test_group_tables_at_scale(dkt, groups_env):
     xyz, lev = dkt.trees.moving_ball_tree(dim, 7, md, use_torch=True)
     op = dkt.Operator.dense(dkt.operators.laplace_kref(dim, 1), dim - 2.0)
     outs = []
-    for gg in (0, 2, 3):
-        os.environ["DKT_GROUPS"] = str(gg)
+    for gg in ("0", "2", "3", "2,1"):
+        os.environ["DKT_GROUPS"] = gg
         da = dkt.DA(xyz, lev, dim, 1, md)
         u = torch.rand(da.n_nodes, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 2 - 1
         v = torch.zeros_like(u)
