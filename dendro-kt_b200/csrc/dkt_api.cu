@@ -238,12 +238,24 @@ extern "C"
     return DKT_OK;
   }
 
+  int dkt_p2p_attach_local(dkt_da **das, int n)
+  {
+    if (!das || n < 2 || n > 64) { set_error("bad arguments"); return DKT_ERR_INVALID; }
+    std::vector<Dist *> r(n, nullptr);
+    for (int i = 0; i < n; i++)
+    {
+      if (!das[i]) { set_error("NULL da"); return DKT_ERR_INVALID; }
+      r[i] = &das[i]->dist;
+    }
+    return p2p_attach_local(r.data(), n);
+  }
+
   int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags)
   {
     if (!da || !op || !in || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
     DA &d = da->d;
     CKA(cudaSetDevice(d.device));
-    if (da->dist.active && da->dist.nranks > 1 && !da->dist.comm) { set_error("dry-run partition: no communicator"); return DKT_ERR_INVALID; }
+    if (da->dist.active && da->dist.nranks > 1 && !da->dist.comm && !da->dist.p2p) { set_error("dry-run partition: no communicator"); return DKT_ERR_INVALID; }
     const size_t bytes = (da->dist.active ? da->dist.nOwned : d.nNodes) * sizeof(double);
     const double *din = in;
     double *dout = out;

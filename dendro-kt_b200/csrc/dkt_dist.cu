@@ -356,29 +356,24 @@ struct P2PInfo
   uint64_t nGhost, totalSend;
   uint64_t recv_off[P2P_MAX_RANKS + 1], send_off[P2P_MAX_RANKS + 1];
 };
-static int setup_p2p(DA &g, Dist &d)
+static int p2p_alloc(Dist &d, P2PInfo &mine)
 {
-  const int R = d.nranks, me = d.rank;
+  const int R = d.nranks;
   if (R > P2P_MAX_RANKS) { set_error("DKT_DIST_P2P: at most 64 ranks"); return DKT_ERR_UNSUPPORTED; }
   const uint64_t nGhost = d.recv_off[R], totalSend = d.send_off[R];
   const size_t bytes = P2P_FLAG_BYTES + (nGhost + totalSend + 1) * sizeof(double);
   CK(cudaMalloc((void **)&d.xbuf, bytes));
   CK(cudaMemset(d.xbuf, 0, bytes));
-  std::vector<P2PInfo> info(R);
-  P2PInfo &mine = info[me];
   std::memset(&mine, 0, sizeof(mine));
-  CK(cudaIpcGetMemHandle(&mine.handle, d.xbuf));
   mine.nGhost = nGhost;
   mine.totalSend = totalSend;
   for (int p = 0; p <= R; p++) { mine.recv_off[p] = d.recv_off[p]; mine.send_off[p] = d.send_off[p]; }
-  char *dinfo = nullptr;
-  CK(cudaMalloc((void **)&dinfo, sizeof(P2PInfo) * R));
-  CK(cudaMemcpyAsync(dinfo + sizeof(P2PInfo) * me, &mine, sizeof(P2PInfo), cudaMemcpyHostToDevice, g.stream));
-  NCK(g_nccl.AllGather(dinfo + sizeof(P2PInfo) * me, dinfo, sizeof(P2PInfo), NCCL_UINT8, (ncclComm_p)d.comm, g.stream));
-  CK(cudaMemcpyAsync(info.data(), dinfo, sizeof(P2PInfo) * R, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
-  cudaFree(dinfo);
-  d.peer_base.assign(R, nullptr);
+  return DKT_OK;
+}
+// base[p]: rank p's xbuf as seen from this process (nullptr: no exchange with p), info[p]: its segment offsets
+static int p2p_wire(Dist &d, const std::vector<P2PInfo> &info, const std::vector<void *> &base)
+{
+  const int R = d.nranks, me = d.rank;
   std::vector<double *> xr(R, nullptr), xw(R, nullptr);
   std::vector<uint32_t *> fr(R, nullptr), fw(R, nullptr);
   for (int p = 0; p < R; p++)
@@ -392,14 +387,12 @@ static int setup_p2p(DA &g, Dist &d)
       return DKT_ERR_INVALID;
     }
     if (!sc && !rcv) continue;
-    void *base = nullptr;
-    CK(cudaIpcOpenMemHandle(&base, info[p].handle, cudaIpcMemLazyEnablePeerAccess));
-    d.peer_base[p] = base;
-    double *x = (double *)((char *)base + P2P_FLAG_BYTES);
+    if (!base[p]) { set_error("DKT_DIST_P2P: no mapping of the exchange buffer of rank " + std::to_string(p)); return DKT_ERR_INVALID; }
+    double *x = (double *)((char *)base[p] + P2P_FLAG_BYTES);
     xr[p] = x + info[p].recv_off[me];                    // peer p's ghost values owned by me
     xw[p] = x + info[p].nGhost + info[p].send_off[me];   // partial sums of p's owned nodes that I ghost
-    fr[p] = (uint32_t *)base + me;
-    fw[p] = (uint32_t *)base + P2P_MAX_RANKS + me;
+    fr[p] = (uint32_t *)base[p] + me;
+    fw[p] = (uint32_t *)base[p] + P2P_MAX_RANKS + me;
   }
   CK(cudaMalloc((void **)&d.d_peer_xr, R * sizeof(double *)));
   CK(cudaMalloc((void **)&d.d_peer_xw, R * sizeof(double *)));
@@ -416,6 +409,55 @@ static int setup_p2p(DA &g, Dist &d)
   CK(cudaMemcpy(d.d_send_off, d.send_off.data(), (R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d.d_recv_off, d.recv_off.data(), (R + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
   d.p2p = true;
+  return DKT_OK;
+}
+static int setup_p2p(DA &g, Dist &d)
+{
+  const int R = d.nranks, me = d.rank;
+  std::vector<P2PInfo> info(R);
+  int rc = p2p_alloc(d, info[me]);
+  if (rc) return rc;
+  CK(cudaIpcGetMemHandle(&info[me].handle, d.xbuf));
+  char *dinfo = nullptr;
+  CK(cudaMalloc((void **)&dinfo, sizeof(P2PInfo) * R));
+  CK(cudaMemcpyAsync(dinfo + sizeof(P2PInfo) * me, &info[me], sizeof(P2PInfo), cudaMemcpyHostToDevice, g.stream));
+  NCK(g_nccl.AllGather(dinfo + sizeof(P2PInfo) * me, dinfo, sizeof(P2PInfo), NCCL_UINT8, (ncclComm_p)d.comm, g.stream));
+  CK(cudaMemcpyAsync(info.data(), dinfo, sizeof(P2PInfo) * R, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  cudaFree(dinfo);
+  d.peer_base.assign(R, nullptr);
+  std::vector<void *> base(R, nullptr);
+  for (int p = 0; p < R; p++)
+  {
+    if (p == me) continue;
+    if (d.send_off[p + 1] == d.send_off[p] && d.recv_off[p + 1] == d.recv_off[p]) continue;
+    CK(cudaIpcOpenMemHandle(&base[p], info[p].handle, cudaIpcMemLazyEnablePeerAccess));
+    d.peer_base[p] = base[p];
+  }
+  return p2p_wire(d, info, base);
+}
+// Single-process variant for tests: the R ranks of one partition live in this process (dry-run DAs, possibly all on
+// one GPU) and see each other's exchange buffers directly - the same kernels and protocol without IPC and NCCL.
+int p2p_attach_local(Dist **ranks, int R)
+{
+  std::vector<P2PInfo> info(R);
+  std::vector<void *> base(R, nullptr);
+  for (int p = 0; p < R; p++)
+  {
+    if (!ranks[p] || !ranks[p]->active || ranks[p]->nranks != R || ranks[p]->rank != p || ranks[p]->p2p)
+    {
+      set_error("p2p_attach_local: pass the dry-run DAs of ranks 0..R-1 of one partition, once");
+      return DKT_ERR_INVALID;
+    }
+    int rc = p2p_alloc(*ranks[p], info[p]);
+    if (rc) return rc;
+    base[p] = ranks[p]->xbuf;
+  }
+  for (int p = 0; p < R; p++)
+  {
+    int rc = p2p_wire(*ranks[p], info, base);
+    if (rc) return rc;
+  }
   return DKT_OK;
 }
 

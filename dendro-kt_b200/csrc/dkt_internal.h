@@ -146,6 +146,7 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id);
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
 void free_dist(Dist &d);
 int nccl_unique_id(void *out128);
+int p2p_attach_local(Dist **ranks, int R);
 // red[0], red[1]: sum over ranks; red[2]: max over ranks (device buffer of 4 doubles)
 int dist_allreduce(Dist &d, double *red, cudaStream_t s);
 int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_b, int max_iter, double *tol, double scale,

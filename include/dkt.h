@@ -123,6 +123,11 @@ int dkt_nccl_unique_id(void *out128);
 int dkt_da_create_dist(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
                        uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, int rank, int nranks,
                        const void *nccl_id, dkt_da **out);
+/* Test hook of the peer-memory exchange (DKT_DIST_P2P): das[0..n-1] are the DKT_DIST_DRYRUN DAs of
+ * ranks 0..n-1 of ONE partition, all created in this process; their exchange buffers are wired to each other directly
+ * (no IPC, no NCCL), after which dkt_matvec works on them with device vectors - enqueue the matvec of every rank before
+ * synchronising any of them.  No reference counterpart. */
+int dkt_p2p_attach_local(dkt_da **das, int n);
 int dkt_da_export_owned_ids(const dkt_da *da, uint32_t *ids);
 /* send_counts[p] = owned nodes rank p ghosts, recv_counts[p] = this rank's ghosts owned by p (n_ranks each) */
 int dkt_da_export_exchange(const dkt_da *da, uint64_t *send_counts, uint64_t *recv_counts);
