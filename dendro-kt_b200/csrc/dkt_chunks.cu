@@ -94,6 +94,7 @@ constexpr uint32_t META_LEN = 0x1FFu;
 constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty: only read by this chunk)
 constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
+constexpr uint32_t REC_SHARED = 0x80000000u, REC_BDY = 0x40000000u, REC_GID = 0x3FFFFFFFu;  // group sets: 4-byte node records
 constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
 constexpr int GRP_TPB = 128;                // threads (= units per chunk at most) of the group kernels
 // units per chunk of a group set with `spu` slots per unit: what the block sort holds, rounded down to whole warps
@@ -185,12 +186,13 @@ __global__ void k_unit_slots_elem(const uint32_t *e2n, const uint32_t *pnode, co
 
 // One CTA per chunk of `upc` units with `spu` slots each (U is unit-major).  WRITE == false: only report the
 // chunk's node count and longest run.  split16: the slot words are stored as two 16-bit arrays (node rank /
-// position), two slots per 32-bit word, and the node records as 8-byte {gid, meta} pairs (group sets).
+// position), two slots per 32-bit word, the node records as ONE 32-bit word gid | boundary bit | shared bit, and the jd table is
+// followed by cnt[k] = #nodes with a run longer than k, which replaces the run length of the records (group sets).
 template <bool WRITE, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16, const uint32_t *refcnt, const uint8_t *isbdy,
               const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out, uint32_t *slot, uint16_t *rk16,
-              uint16_t *ps16, uint32_t *gid_out, uint16_t *meta_out, uint2 *rec_out, uint16_t *jd_out)
+              uint16_t *ps16, uint32_t *gid_out, uint16_t *meta_out, uint32_t *rec_out, uint16_t *jd_out)
 {
   constexpr int CAP = SORT_THREADS * ITEMS;
   using SortPairs = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS, uint16_t>;
@@ -209,6 +211,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
   __shared__ uint16_t s_cw[CAP + 1];           // by gid-rank: number of WRITING references sorted before the node
   __shared__ int s_hist[MAX_LEN + 2];
   __shared__ int s_jd[MAX_LEN + 2];
+  __shared__ int s_cnt[MAX_LEN + 2];          // #nodes with run length > k
   __shared__ int s_total, s_P, s_maxlen;
 
   const uint64_t c = blockIdx.x;
@@ -344,8 +347,10 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
     for (int k = ml; k >= 0; k--)
     {
       s_jd[k] = above;  // #nodes with len > k
+      s_cnt[k] = above;
       above += s_hist[k];
     }
+    for (int k = ml + 1; k < MAX_LEN + 2; k++) s_cnt[k] = 0;
     // diagonal k starts at a position congruent to k modulo 16 (the number of 8-byte bank pairs):
     // the k-th contributions to one node - written by sibling elements in the same instruction
     // under the XOR slot schedule - then fall into distinct banks
@@ -362,7 +367,14 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
   }
   __syncthreads();
   const uint64_t noff = node_off[c];
-  for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS) jd_out[c * (uint64_t)jdStride + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
+  if (!split16)
+    for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS) jd_out[c * (uint64_t)jdStride + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
+  else  // group sets: [jd | cnt] per chunk; the node records carry no run length, cnt[] gives it (nodes are ranked by it)
+    for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS)
+    {
+      jd_out[c * (uint64_t)(2 * jdStride) + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
+      jd_out[c * (uint64_t)(2 * jdStride) + jdStride + k] = (uint16_t)s_cnt[min(k, MAX_LEN + 1)];
+    }
   // absent node: read the chunk's zero entry un[nloc], write to the trash position behind the diagonals
   const uint32_t trash = (uint32_t)s_jd[MAX_LEN + 1];
 #pragma unroll
@@ -400,7 +412,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
         gid_out[noff + nr] = key[i];
         meta_out[noff + nr] = (uint16_t)m;
       }
-      else rec_out[noff + nr] = make_uint2(key[i], m);
+      else rec_out[noff + nr] = key[i] | ((m & META_SHARED) ? REC_SHARED : 0u) | ((m & META_BDY) ? REC_BDY : 0u);
     }
   }
 }
@@ -472,11 +484,11 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   {
     CK(cudaMalloc((void **)&cs.d_rk16, nslotsAll * sizeof(uint16_t)));
     CK(cudaMalloc((void **)&cs.d_ps16, nslotsAll * sizeof(uint16_t)));
-    CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 1) * sizeof(uint2)));
+    CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
   }
-  CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * sizeof(uint16_t)));
+  CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * (split16 ? 2 : 1) * sizeof(uint16_t)));
   DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, split16, refcnt, da.d_node_isbdy, off, (int)cs.jdStride, nullptr,
-                                                              nullptr, cs.d_slot, cs.d_rk16, cs.d_ps16, cs.d_gid, cs.d_meta, (uint2 *)cs.d_rec,
+                                                              nullptr, cs.d_slot, cs.d_rk16, cs.d_ps16, cs.d_gid, cs.d_meta, (uint32_t *)cs.d_rec,
                                                               cs.d_jd);
   g_launches++;
   CK(cudaStreamSynchronize(da.stream));
@@ -822,6 +834,7 @@ static int groups_requested(const DA &da, int &gH)
 int build_chunks(DA &da)
 {
   if (da.nNodes >= 0x7FFFFFFFull) { set_error("more than 2^31 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
+  if (getenv("DKT_GROUPS") && da.nNodes >= 0x3FFFFFFFull) { set_error("DKT_GROUPS: more than 2^30 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
   CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
   DKT_LAUNCH(k_child_numbers, nblk(da.nMv), 256, 0, da.stream)(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth, da.d_mv_child);
   g_launches++;
@@ -1014,7 +1027,7 @@ struct Mv3Params
   const uint8_t *child;  // Morton child numbers of the set's elements
   const uint32_t *fmask; // hanging set: filled own slots (slot order)
   const uint32_t *rk16, *ps16;   // group sets: 16-bit node ranks / positions, two slots per word
-  const uint2 *rec;              // group sets: {gid, meta} per chunk node
+  const uint32_t *rec;           // group sets: gid | boundary bit 30 | shared bit 31 per chunk node
   const uint64_t *fmask64;       // hanging group sets: filled own lattice slots
   uint32_t nSet, nChunks, elemsPerChunk, xcap, ncap, jdStride;
   int q1mask;
@@ -1172,10 +1185,16 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 #else
 inline void cp_async8(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 8); }
+inline void cp_async4(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 4); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 #endif
@@ -1453,7 +1472,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
 // group additionally reads the 2^DIM parent nodes once, interpolates them to the whole lattice (exact order-1
 // interpolation: midpoints) and scatters one masked transposed sum.  Quirk Q1 (FEM/include/matvec.h:517) is
 // applied per child at run time from the 64-bit fill mask, so every parent slot is a writing slot here.
-// Pipeline per chunk (two barriers): node records {gid, meta} are staged in shared memory by cp.async - every
+// Pipeline per chunk (two barriers): the 4-byte node records are staged in shared memory by cp.async - every
 // thread copies, consumes and later overwrites only its OWN records -, the gather of chunk i+1 is issued right
 // after barrier A and stays in flight during the whole of chunk i.
 template <int DIM, int G>
@@ -1550,8 +1569,8 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
   DKT_DYN_SMEM(double, sm);
   double *X = sm;                                      // [xcap]
   double *unb = sm + p.xcap;                           // [2][ncap]
-  uint2 *recb = (uint2 *)(sm + p.xcap + 2 * p.ncap);   // [2][ncap]
-  int *jdb = (int *)(recb + 2 * p.ncap);               // [2][jdStride]
+  int *jdb = (int *)(sm + p.xcap + 2 * p.ncap);        // [2][jd[jdStride] | cnt[jdStride]]
+  uint32_t *recb = (uint32_t *)(jdb + 4 * p.jdStride); // [2][ncap]
 
   const int tid = threadIdx.x;
   const uint32_t E = p.elemsPerChunk;
@@ -1559,21 +1578,21 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
   if (c >= p.nChunks) return;
 
   auto issue_rec = [&](uint64_t oa, int nloc, int b) {
-    uint2 *dst = recb + b * p.ncap;
-    for (int n = tid; n < nloc; n += TPB) cp_async8(dst + n, p.rec + oa + n);
+    uint32_t *dst = recb + b * p.ncap;
+    for (int n = tid; n < nloc; n += TPB) cp_async4(dst + n, p.rec + oa + n);
   };
   auto issue_gather = [&](uint64_t cc, int nloc, int b) {
     double *un = unb + b * p.ncap;
-    const uint2 *rec = recb + b * p.ncap;
+    const uint32_t *rec = recb + b * p.ncap;
     if (tid == 0) un[nloc] = 0.0;  // the entry absent nodes read
     for (int n = tid; n < nloc; n += TPB)
     {
-      const uint2 r = rec[n];
-      if (DIRI && (r.y & META_BDY)) un[n] = 0.0;
-      else cp_async8(un + n, p.in + r.x);
+      const uint32_t r = rec[n];
+      if (DIRI && (r & REC_BDY)) un[n] = 0.0;
+      else cp_async8(un + n, p.in + (r & REC_GID));
     }
-    int *jdn = jdb + b * p.jdStride;
-    for (int k = tid; k < (int)p.jdStride; k += TPB) jdn[k] = p.jd[cc * (uint64_t)p.jdStride + k];
+    int *jdn = jdb + b * 2 * p.jdStride;
+    for (int k = tid; k < 2 * (int)p.jdStride; k += TPB) jdn[k] = p.jd[cc * (uint64_t)(2 * p.jdStride) + k];
   };
   uint32_t wr[NW];
   int levU = 0;
@@ -1617,7 +1636,7 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
   while (true)
   {
     double *un = unb + buf * p.ncap;
-    const int *jd = jdb + buf * p.jdStride;
+    const int *jd = jdb + buf * 2 * p.jdStride;
     cp_async_wait_all();
     __syncthreads();  // A: un/jd of this chunk visible, own records of the next chunk landed; X and un[buf^1] free
     const uint64_t cnn = cn + stride;
@@ -1789,38 +1808,42 @@ __global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_R
     __syncthreads();  // B: X complete
     // ---- T4: own nodes of this chunk
     {
-      // four nodes per thread at a time: independent accumulation chains, one jd[j] load for the four.  Nodes are
-      // ranked by run length (descending), so the first of the four has the longest run.
-      const uint2 *rec = recb + buf * p.ncap;
-      for (int base = tid; base < nlocC; base += 4 * TPB)
+      // four nodes per thread at a time: independent accumulation chains, one jd[j] / cnt[j] load for the four.  Nodes
+      // are ranked by run length (descending) and cnt[j] = #nodes with a run longer than j, so node n has a j-th
+      // contribution iff n < cnt[j]; nodes >= cnt[0] are only read by this chunk.
+      const uint32_t *rec = recb + buf * p.ncap;
+      const int *cnt = jd + p.jdStride;
+      const int cnt0 = cnt[0];
+      for (int base = tid; base < cnt0; base += 4 * TPB)
       {
-        uint2 r[4];
-        int len[4];
+        uint32_t r[4];
         double acc[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
           const int n = base + i * TPB;
-          r[i] = make_uint2(0u, 0u);
-          if (n < nlocC) r[i] = rec[n];
-          len[i] = (int)(r[i].y & META_LEN);
-          acc[i] = len[i] ? X[n] : 0.0;  // jd[0] == 0
+          r[i] = 0u;
+          acc[i] = 0.0;
+          if (n < cnt0)
+          {
+            r[i] = rec[n];
+            acc[i] = X[n];  // jd[0] == 0
+          }
         }
-        const int lmax = len[0];
-        for (int j = 1; j < lmax; j++)
+        for (int j = 1; base < cnt[j]; j++)
         {
-          const int off = jd[j] + base;
+          const int off = jd[j] + base, cj = cnt[j];
 #pragma unroll
           for (int i = 0; i < 4; i++)
-            if (j < len[i]) acc[i] += X[off + i * TPB];
+            if (base + i * TPB < cj) acc[i] += X[off + i * TPB];
         }
 #pragma unroll
         for (int i = 0; i < 4; i++)
         {
-          if (len[i] == 0) continue;  // beyond the chunk's nodes, or only read by this chunk
-          if (DIRI && (r[i].y & META_BDY)) continue;
-          if (r[i].y & META_SHARED) atomicAdd(p.out + r[i].x, acc[i]);
-          else p.out[r[i].x] = acc[i];
+          if (base + i * TPB >= cnt0) continue;
+          if (DIRI && (r[i] & REC_BDY)) continue;
+          if (r[i] & REC_SHARED) atomicAdd(p.out + (r[i] & REC_GID), acc[i]);
+          else p.out[r[i] & REC_GID] = acc[i];
         }
       }
     }
@@ -1845,14 +1868,14 @@ static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
   constexpr int SPU = (GP::LP + (HANG ? GP::N : 0) + 1) & ~1;
   constexpr int TPB = grp_tpb(SPU);
   if (cs.spu != SPU || (int)cs.elemsPerChunk > TPB) { set_error("internal: group set does not match its kernel"); return DKT_ERR_INVALID; }
-  p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint2 *)cs.d_rec; p.jd = cs.d_jd;
+  p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint32_t *)cs.d_rec; p.jd = cs.d_jd;
   p.node_off = cs.d_node_off; p.lev = cs.lev; p.fmask64 = cs.fmask64;
   p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
   p.xcap = (uint32_t)cs.elemsPerChunk * SPU + 258u;  // + padding of the first 16 diagonals + the trash position
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
-  const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.ncap * sizeof(uint2) +
-                      2 * (size_t)p.jdStride * sizeof(int);
+  const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.ncap * sizeof(uint32_t) +
+                      4 * (size_t)p.jdStride * sizeof(int);
   auto kern = k_mvg<DIM, G, OPKIND, DIRI, HANG, TPB>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;

@@ -55,7 +55,7 @@ struct ChunkSet
   int kind = 0, g = 0;
   int spu = 0;                     // slots per unit (padded to an even number for group sets)
   uint16_t *d_rk16 = nullptr, *d_ps16 = nullptr;  // node rank / position of every slot, two slots per 32-bit word
-  void *d_rec = nullptr;           // [totalNodes] {gid, meta} (uint2)
+  void *d_rec = nullptr;           // [totalNodes] uint32: gid | boundary bit 30 | shared bit 31 (d_jd then holds [jd | cnt] per chunk)
   const uint64_t *fmask64 = nullptr; // hanging group sets: filled own lattice slots
   std::vector<void *> owned;       // device buffers freed with the set
 };
