@@ -209,7 +209,7 @@ def run_groups_probe_subprocess(args, g="2", timeout=180):
                 return json.loads(ln)
         return {"groups": g, "error": ("rc=%d " % r.returncode) + (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
     except subprocess.TimeoutExpired:
-        return {"groups": g, "error": "timeout after %d s" % timeout}
+        return {"groups": g, "error": "timeout after %d s" % int(timeout)}
     except Exception as e:
         return {"groups": g, "error": repr(e)[:300]}
 
@@ -377,7 +377,13 @@ def run_gpu(args):
         if args.experimental and world == 1 and args.groups == "0":
             # opt-in sibling-group tables (DKT_GROUPS, validated against the oracle in the CPU emulation, tests/test_emu_chunks.py):
             # timed in a separate process AFTER the headline measurement; informational only
-            line["experimental_groups"] = [run_groups_probe_subprocess(args, g=g, timeout=150) for g in ("2", "2,1", "3,2")]
+            deadline = time.time() + 120.0  # the whole experimental leg is bounded; what does not fit is skipped
+            probes = []
+            for g in ("2", "2,1", "3,2"):
+                left = deadline - time.time()
+                probes.append(run_groups_probe_subprocess(args, g=g, timeout=min(90.0, left)) if left > 20.0
+                              else {"groups": g, "error": "skipped: time budget of the experimental leg used up"})
+            line["experimental_groups"] = probes
         print(json.dumps(line))
     da.close()
     if dist is not None:
