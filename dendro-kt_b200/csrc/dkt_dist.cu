@@ -18,6 +18,7 @@
 // The global tables are freed afterwards.  (A build whose memory scales with the local part only
 // is future work; the matvec itself is fully partitioned.)
 #include "dkt_internal.h"
+#include "dkt_p2p.cuh"
 
 #include <cub/cub.cuh>
 
@@ -244,64 +245,6 @@ __global__ void k_unpack_add(double *v, const uint32_t *idx, uint64_t n, const d
   if (i < n) atomicAdd(v + idx[i], buf[i]);
 }
 
-// ---- peer-memory exchange (DKT_DIST_P2P=1) ---------------------------------------------------------------
-// Every rank owns one IPC-exported buffer  [flagR[64] flagW[64] .. 1 KiB | xr: ghost values, by owner | xw: partial
-// sums coming back, by ghosting rank]  and maps the peers' buffers.  A "put" kernel gathers and stores straight into
-// the peers' receive regions over NVLink (pack + send in one kernel), a one-block kernel then publishes this matvec's
-// epoch in the peers' flag words, and the consumer waits for the epoch right before it needs the data - by then it
-// has normally arrived behind the interior elements.  One stream, no NCCL kernel competing for SMs.
-// Re-use is safe without double buffering: a rank's put of matvec e+1 into a peer follows its wait for that peer's
-// write-back flag of matvec e, which the peer raised after it had consumed the data of matvec e.
-constexpr size_t P2P_FLAG_BYTES = 1024;
-constexpr int P2P_MAX_RANKS = 64;
-__global__ void k_p2p_put(const double *src, const uint32_t *idx, uint64_t n, const uint64_t *seg_off, double *const *peer_dst, int nranks)
-{
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int p = 0;
-  while (p + 1 < nranks && i >= seg_off[p + 1]) p++;  // segment of peer p: [seg_off[p], seg_off[p+1])
-  peer_dst[p][i - seg_off[p]] = idx ? src[idx[i]] : src[i];
-  __threadfence_system();
-}
-__global__ void k_p2p_signal(uint32_t *const *peer_flag, const uint64_t *seg_off, int nranks, uint32_t epoch)
-{
-  const int p = threadIdx.x;
-  if (p >= nranks || seg_off[p + 1] == seg_off[p]) return;  // nothing was sent to p
-  __threadfence_system();
-  *(volatile uint32_t *)peer_flag[p] = epoch;
-}
-// every block waits for the epoch of all peers that send to this rank (about 2 s at most, then *err = 1)
-__device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, int *err)
-{
-  const int p = threadIdx.x;
-  if (p < nranks && seg_off[p + 1] != seg_off[p])
-  {
-    const long long t0 = clock64();
-    while ((int32_t)(flags[p] - epoch) < 0)
-    {
-      __nanosleep(100);
-      if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1); break; }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-}
-__global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
-                                double *dst, uint64_t n, int *err)
-{
-  p2p_wait(flags, seg_off, nranks, epoch, err);
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __ldcg(x + i);
-}
-// several peers may return contributions to the same owned node -> atomic
-__global__ void k_p2p_wait_add(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
-                               double *v, const uint32_t *idx, uint64_t n, int *err)
-{
-  p2p_wait(flags, seg_off, nranks, epoch, err);
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(v + idx[i], __ldcg(x + i));
-}
-
 #define LAUNCHS(kern, n, stream, ...)                                          \
   do                                                                           \
   {                                                                            \
@@ -350,12 +293,6 @@ void free_dist(Dist &d)
 
 // Peer-memory exchange: allocate the exchange buffer, trade IPC handles and segment offsets through the (already
 // initialised) NCCL communicator, map the peers' buffers and build the device pointer tables.
-struct P2PInfo
-{
-  cudaIpcMemHandle_t handle;
-  uint64_t nGhost, totalSend;
-  uint64_t recv_off[P2P_MAX_RANKS + 1], send_off[P2P_MAX_RANKS + 1];
-};
 static int p2p_alloc(Dist &d, P2PInfo &mine)
 {
   const int R = d.nranks;
@@ -374,25 +311,13 @@ static int p2p_alloc(Dist &d, P2PInfo &mine)
 static int p2p_wire(Dist &d, const std::vector<P2PInfo> &info, const std::vector<void *> &base)
 {
   const int R = d.nranks, me = d.rank;
-  std::vector<double *> xr(R, nullptr), xw(R, nullptr);
-  std::vector<uint32_t *> fr(R, nullptr), fw(R, nullptr);
-  for (int p = 0; p < R; p++)
+  std::vector<double *> xr, xw;
+  std::vector<uint32_t *> fr, fw;
+  std::string why;
+  if (!p2p_tables(me, R, d.send_off.data(), d.recv_off.data(), info.data(), base.data(), xr, xw, fr, fw, why))
   {
-    if (p == me) continue;
-    const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
-    // both sides of every list were derived from the same global tables: they must agree
-    if (info[p].recv_off[me + 1] - info[p].recv_off[me] != sc || info[p].send_off[me + 1] - info[p].send_off[me] != rcv)
-    {
-      set_error("DKT_DIST_P2P: send/receive lists of ranks " + std::to_string(me) + " and " + std::to_string(p) + " disagree");
-      return DKT_ERR_INVALID;
-    }
-    if (!sc && !rcv) continue;
-    if (!base[p]) { set_error("DKT_DIST_P2P: no mapping of the exchange buffer of rank " + std::to_string(p)); return DKT_ERR_INVALID; }
-    double *x = (double *)((char *)base[p] + P2P_FLAG_BYTES);
-    xr[p] = x + info[p].recv_off[me];                    // peer p's ghost values owned by me
-    xw[p] = x + info[p].nGhost + info[p].send_off[me];   // partial sums of p's owned nodes that I ghost
-    fr[p] = (uint32_t *)base[p] + me;
-    fw[p] = (uint32_t *)base[p] + P2P_MAX_RANKS + me;
+    set_error("DKT_DIST_P2P: " + why);
+    return DKT_ERR_INVALID;
   }
   CK(cudaMalloc((void **)&d.d_peer_xr, R * sizeof(double *)));
   CK(cudaMalloc((void **)&d.d_peer_xw, R * sizeof(double *)));

@@ -111,6 +111,11 @@ inline void __syncthreads() { emu::yield(); }
 template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+inline void __threadfence_system() {}
+inline void __nanosleep(unsigned) {}
+inline long long clock64() { static long long c = 0; return c += 1000; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
 using std::max;
 using std::min;
 
