@@ -125,3 +125,36 @@ def test_emulated_two_level_groups(name, groups):
     v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True, groups=groups,
                              order=2, phased_seed=(5 if len(t.mv_lev) < 50000 else None))
     assert rel(v, ref) <= TOL
+
+
+@pytest.mark.parametrize("seed", [3, 8, 15, 21])
+def test_emulated_random_trees(seed):
+    """random 2:1-balanced trees (refinement towards random spheres, some at a domain corner -> phantom elements),
+    random group spec / phase layout / fiber order: the emulated chunk path against the oracle"""
+    import dkt
+    rng = np.random.default_rng(seed)
+    dim = int(rng.choice([2, 3, 3, 4]))
+    md = 8
+    maxl = {2: 7, 3: 5, 4: 4}[dim]
+    pts = rng.uniform(0.0, 1.0, (int(rng.integers(1, 4)), dim))
+    if rng.random() < 0.5:
+        pts[0] = rng.choice([0.0, 1.0], dim)
+    rad = rng.uniform(0.0, 0.3, len(pts))
+
+    def g(ctr):
+        d = np.full(len(ctr), 1e9)
+        for p, r in zip(pts, rad):
+            d = np.minimum(d, np.abs(np.abs(ctr - p).max(axis=1) - r))
+        return d
+
+    xyz, lev = dkt.trees._refine(np, dim, md, int(rng.integers(1, 3)), maxl, g)
+    t = flat.build_tables(xyz, lev, dim, 1, md)
+    if t.tree_class == "U" or len(t.mv_lev) > 40000:
+        pytest.skip("class-U or too large for the CPU suite")
+    u = rng.uniform(-1, 1, len(t.node_lev))
+    K = flat.laplace_kref(dim, 1) + 0.3 * flat.mass_kref(dim, 1)
+    ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True)
+    for spec in {2: ["0", "2"], 3: ["0", "3", "3,2"], 4: ["0", "2", "2,1", "3,2"]}[dim]:
+        v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True, groups=spec, order=int(rng.integers(0, 3)),
+                                 phased_seed=(None if rng.random() < 0.5 else int(rng.integers(0, 100))))
+        assert rel(v, ref) <= TOL, spec
