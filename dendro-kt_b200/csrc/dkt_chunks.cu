@@ -96,7 +96,10 @@ constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
 constexpr uint32_t REC_SHARED = 0x80000000u, REC_BDY = 0x40000000u, REC_GID = 0x3FFFFFFFu;  // group sets: 4-byte node records
 constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
-constexpr int GRP_TPB = 128;                // threads (= units per chunk at most) of the group kernels
+#ifndef DKT_GRP_TPB
+#define DKT_GRP_TPB 128  // threads (= units per chunk at most) of the group kernels; 96 lets three CTAs of regular quads share an SM
+#endif
+constexpr int GRP_TPB = DKT_GRP_TPB;
 // units per chunk of a group set with `spu` slots per unit: what the block sort holds, rounded down to whole warps
 // when that costs at most an eighth; threads of its kernel: the next multiple of 32
 constexpr int grp_upc(int spu)
@@ -118,8 +121,9 @@ constexpr int grp_tpb(int spu) { return (grp_upc(spu) + 31) & ~31; }
 #ifndef DKT_HANG_MINB
 #define DKT_HANG_MINB 4
 #endif
-// resident CTAs per SM the group kernels are compiled for.  ptxas, 4-D quads: 2 -> 212 (regular) / 255 (hanging)
-// registers, no spills; 3 -> 168 registers, 64 B / ~0.9 KB of spills
+// resident CTAs per SM the group kernels are compiled for.  ptxas, 4-D: 2 -> 220 (regular quads) / 255 (hanging quads) /
+// 220 (hanging pairs) registers, no spills; 3 -> 168 registers: regular quads and hanging pairs without spills, hanging
+// quads 0.6 KB of spills (profiles/r01_ptxas_groups.txt)
 #ifndef DKT_GRP_RSHARE
 #define DKT_GRP_RSHARE 1  // regular groups: shared butterflies along the XOR-permuted dimensions (see k_mvg)
 #endif
