@@ -29,6 +29,25 @@ for st in 2 4; do
   echo "bench groups=2 streams=$st rc=$?" | tee -a $out/summary.txt
 done
 DKT_MV_STREAMS=2 timeout 600 python bench.py --groups 0 --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_g0_s2.json 2> $out/bench_g0_s2.err
+# compile-time variants, built BEFORE the gpurun call in the container (they travel with the snapshot), e.g.
+#   tools/build_variant.sh m3  -DDKT_GRP_MINB_REG=3 -DDKT_GRP_MINB_HANG=3                 # 168-register budget
+#   tools/build_variant.sh t96 -DDKT_GRP_TPB=96 -DDKT_GRP_MINB_REG=3 -DDKT_GRP_MINB_HANG=3 # three CTAs of regular quads per SM
+for L in dendro-kt_b200/lib/libdkt_*.so; do
+  [ -f "$L" ] || continue
+  v=$(basename $L .so)
+  for g in 2 2,1; do
+    DKT_LIB=$PWD/$L timeout 600 python bench.py --groups $g --steps 20 --warmup 5 --no-experimental --no-cpu-baseline > $out/bench_${v}_g$g.json 2> $out/bench_${v}_g$g.err
+    echo "bench $v groups=$g rc=$?" | tee -a $out/summary.txt
+    python - <<PY
+import json
+try:
+    d = json.loads(open("$out/bench_${v}_g$g.json").read().strip().splitlines()[-1])
+    print("$v groups=$g", "ms", round(d["ms_per_step"], 4), "DOF/s %.3e" % d["value"], "frac", round(d["roofline"]["frac"], 4))
+except Exception as e:
+    print("$v groups=$g", "no result", e)
+PY
+  done
+done
 # launch list (per-kernel device time) and one full capture of the group kernels
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_g2.csv \
   python bench.py --groups 2 --steps 3 --warmup 2 --no-experimental --no-cpu-baseline > $out/ncu_launches.log 2>&1
