@@ -100,15 +100,19 @@ constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only refere
 #define DKT_GRP_TPB 128  // threads (= units per chunk at most) of the group kernels; 96 lets three CTAs of regular quads share an SM
 #endif
 constexpr int GRP_TPB = DKT_GRP_TPB;
-// units per chunk of a group set with `spu` slots per unit: what the block sort holds, rounded down to whole warps
-// when that costs at most an eighth; threads of its kernel: the next multiple of 32
-constexpr int grp_upc(int spu)
+// units per chunk of a group set with `spu` slots per unit (groups of 2^g leaves): what the block sort holds, at most
+// 512 elements in 4-D / 1024 below (the chunk's nodes are double-buffered in shared memory: with more, two CTAs no longer
+// fit on an SM), rounded down to whole warps when that costs at most an eighth; threads of its kernel: the next multiple of 32
+constexpr int grp_upc(int spu, int dim, int g)
 {
-  const int u = (SORT_THREADS * SORT_ITEMS_GRP / spu) < GRP_TPB ? (SORT_THREADS * SORT_ITEMS_GRP / spu) : GRP_TPB;
+  int u = SORT_THREADS * SORT_ITEMS_GRP / spu;
+  if (u > GRP_TPB) u = GRP_TPB;
+  const int cap = (dim >= 4 ? 512 : 1024) >> g;
+  if (u > cap) u = cap;
   const int r = u & ~31;
   return (r > 0 && (u - r) * 8 <= u) ? r : u;
 }
-constexpr int grp_tpb(int spu) { return (grp_upc(spu) + 31) & ~31; }
+constexpr int grp_tpb(int spu, int dim, int g) { return (grp_upc(spu, dim, g) + 31) & ~31; }
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
@@ -765,7 +769,7 @@ static int add_group_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *
   const int LP = L3 << (da.dim - g);
   cs.rows = hang ? 2 : 1; cs.phase = phase; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
   cs.spu = (LP + (hang ? da.N : 0) + 1) & ~1;
-  cs.elemsPerChunk = grp_upc(cs.spu);
+  cs.elemsPerChunk = grp_upc(cs.spu, da.dim, g);
   uint32_t *U = nullptr;
   uint8_t *lev_g = nullptr;
   unsigned long long *fm = nullptr;
@@ -1870,7 +1874,7 @@ static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
 {
   using GP = Grp<DIM, G>;
   constexpr int SPU = (GP::LP + (HANG ? GP::N : 0) + 1) & ~1;
-  constexpr int TPB = grp_tpb(SPU);
+  constexpr int TPB = grp_tpb(SPU, DIM, G);
   if (cs.spu != SPU || (int)cs.elemsPerChunk > TPB) { set_error("internal: group set does not match its kernel"); return DKT_ERR_INVALID; }
   p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint32_t *)cs.d_rec; p.jd = cs.d_jd;
   p.node_off = cs.d_node_off; p.lev = cs.lev; p.fmask64 = cs.fmask64;
