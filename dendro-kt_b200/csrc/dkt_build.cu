@@ -15,9 +15,15 @@
 //   * hanging tables ........ FEM/include/matvec.h:403-457 (parent nodes of level L-1)
 //   * phantom children ...... FEM/include/matvec.h:102-107,340-362 (quirk Q3)
 // Sorting/scans use CUB (construction is one-off; the hot path is in dkt_matvec.cu).
+// Like dkt_chunks.cu this file also compiles under -DDKT_EMU (tests/emu/cuda_emu.h) so that the CPU test-suite can run
+// the table construction against the reference's golden fixtures; the product is never built that way.
 #include "dkt_internal.h"
 
+#ifdef DKT_EMU
+#include "cuda_emu.h"
+#else
 #include <cub/cub.cuh>
+#endif
 
 #include <algorithm>
 #include <cstdio>
@@ -68,12 +74,17 @@ struct Buf
 };
 
 static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+#ifdef DKT_EMU
+#define DKT_BUILD_LAUNCH(kern, grid, stream) ::emu::make_launch_flat(kern, (grid), 256)
+#else
+#define DKT_BUILD_LAUNCH(kern, grid, stream) kern<<<(grid), 256, 0, (stream)>>>
+#endif
 #define LAUNCH(kern, n, ...)                                                       \
   do                                                                               \
   {                                                                                \
     if ((n) > 0)                                                                   \
     {                                                                              \
-      kern<<<nblk(n), 256, 0, da.stream>>>(__VA_ARGS__);                           \
+      DKT_BUILD_LAUNCH(kern, nblk(n), da.stream)(__VA_ARGS__);                     \
       g_launches++;                                                                \
     }                                                                              \
   } while (0)
@@ -169,8 +180,12 @@ __global__ void k_max_level(const uint8_t *lev, uint64_t n, int *out)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   int v = i < n ? lev[i] : 0;
+#ifndef DKT_EMU
   for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+#else
+  if (v > 0) atomicMax(out, v);
+#endif
 }
 
 __global__ void k_elem_keys(const uint32_t *xyz, const uint8_t *lev, uint64_t n, Geo g, uint64_t *key, uint32_t *idx)

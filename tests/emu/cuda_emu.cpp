@@ -24,6 +24,11 @@ State &state()
 void yield()
 {
   State &s = state();
+  if (s.current < 0)
+  {
+    fprintf(stderr, "emu: __syncthreads() in a kernel launched without fibers\n");
+    abort();
+  }
   s.barriers++;
   Fiber &f = s.fibers[s.current];
   swapcontext(&f.ctx, &s.sched);

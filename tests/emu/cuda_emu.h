@@ -26,6 +26,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __shared__ static
+#define __constant__ static
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __restrict__
@@ -101,6 +102,32 @@ struct Launch
 };
 template <typename F>
 Launch<F *> make_launch(F *f, uint64_t grid, unsigned block, size_t smem) { return Launch<F *>{f, (unsigned)grid, block, smem}; }
+// kernels WITHOUT barriers and shared memory (element-wise): the threads run as a plain loop, no fibers
+template <typename F>
+struct LaunchFlat
+{
+  F f;
+  unsigned grid, block;
+  template <typename... A>
+  void operator()(A... args)
+  {
+    gridDim.x = grid;
+    blockDim.x = block;
+    state().current = -2;  // a __syncthreads() here is a bug
+    for (unsigned b = 0; b < grid; b++)
+    {
+      blockIdx.x = b;
+      for (unsigned t = 0; t < block; t++)
+      {
+        threadIdx.x = t;
+        f(args...);
+      }
+    }
+    state().current = -1;
+  }
+};
+template <typename F>
+LaunchFlat<F *> make_launch_flat(F *f, uint64_t grid, unsigned block) { return LaunchFlat<F *>{f, (unsigned)grid, block}; }
 }  // namespace emu
 
 #define DKT_LAUNCH(k, g, b, s, st) ::emu::make_launch(k, (g), (b), (s))
@@ -112,6 +139,7 @@ template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; retu
 template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) {}
 inline long long clock64() { static long long c = 0; return c += 1000; }
@@ -153,6 +181,8 @@ inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { mem
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <typename S> inline cudaError_t cudaMemcpyToSymbol(S &sym, const void *src, size_t n) { memcpy(&sym, src, n); return cudaSuccess; }
 #ifndef DKT_INTERNAL_H
 typedef struct CUevent_st *cudaEvent_t;
 #endif
@@ -160,6 +190,7 @@ enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1 };
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (cudaEvent_t)(void *)0x1; return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)(void *)0x1; return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)(void *)0x1; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
@@ -212,6 +243,56 @@ struct BlockRadixSort
   }
   void Sort(Key (&key)[ITEMS], Value (&val)[ITEMS], int b0 = 0, int b1 = sizeof(Key) * 8) { sort_impl(key, val, b0, b1); }
   void Sort(Key (&key)[ITEMS], int b0 = 0, int b1 = sizeof(Key) * 8) { sort_impl(key, nullptr, b0, b1); }
+};
+// device-wide primitives used by dkt_build.cu (two-phase calling convention: a null temp pointer only asks for its size)
+struct DeviceRadixSort
+{
+  template <typename K, typename V>
+  static cudaError_t SortPairs(void *tmp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, int64_t n, int b0, int b1, cudaStream_t)
+  {
+    if (!tmp) { bytes = 16; return cudaSuccess; }
+    std::vector<int64_t> idx(n);
+    for (int64_t i = 0; i < n; i++) idx[i] = i;
+    const int w = b1 - b0;
+    const uint64_t mask = w >= 64 ? ~0ull : ((1ull << w) - 1);
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return (((uint64_t)kin[a] >> b0) & mask) < (((uint64_t)kin[b] >> b0) & mask); });
+    std::vector<K> kk(n);
+    std::vector<V> vv(n);
+    for (int64_t i = 0; i < n; i++) { kk[i] = kin[idx[i]]; vv[i] = vin[idx[i]]; }
+    for (int64_t i = 0; i < n; i++) { kout[i] = kk[i]; vout[i] = vv[i]; }
+    return cudaSuccess;
+  }
+};
+struct DeviceScan
+{
+  template <typename I, typename O>
+  static cudaError_t ExclusiveSum(void *tmp, size_t &bytes, const I *in, O *out, int64_t n, cudaStream_t)
+  {
+    if (!tmp) { bytes = 16; return cudaSuccess; }
+    O acc = 0;
+    for (int64_t i = 0; i < n; i++) { const O v = (O)in[i]; out[i] = acc; acc += v; }
+    return cudaSuccess;
+  }
+};
+struct DeviceRunLengthEncode
+{
+  template <typename K, typename C, typename N>
+  static cudaError_t Encode(void *tmp, size_t &bytes, const K *in, K *uniq, C *counts, N *nruns, int64_t n, cudaStream_t)
+  {
+    if (!tmp) { bytes = 16; return cudaSuccess; }
+    int64_t r = 0;
+    for (int64_t i = 0; i < n;)
+    {
+      int64_t j = i;
+      while (j < n && in[j] == in[i]) j++;
+      uniq[r] = in[i];
+      counts[r] = (C)(j - i);
+      r++;
+      i = j;
+    }
+    *nruns = (N)r;
+    return cudaSuccess;
+  }
 };
 template <typename T, int THREADS>
 struct BlockScan

@@ -1,0 +1,89 @@
+// The whole single-rank pipeline of libdkt under the CUDA-on-CPU emulation (tests only): dkt_build.cu's table
+// construction + dkt_chunks.cu's chunk tables and kernels, driven like dkt_da_create / dkt_matvec drive them.
+// Lets the CPU test-suite check the PRODUCT's construction code bit-exactly against the reference's golden fixtures.
+#include "dkt_internal.h"
+#include "cuda_emu.h"
+
+#include <string>
+
+namespace dkt
+{
+static std::string g_err;
+uint64_t g_launches = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+int run_matvec(DA &, const dkt_op *, const double *, double *, double, unsigned)
+{
+  set_error("emulation: flat kernels are not part of the emulated build");
+  return DKT_ERR_UNSUPPORTED;
+}
+void free_dist(Dist &) {}
+}  // namespace dkt
+
+using namespace dkt;
+
+extern "C" const char *emu_full_error() { return g_err.c_str(); }
+
+extern "C" void *emu_da_create(int dim, int order, int max_depth, int sfc, const uint32_t *xyz, const uint8_t *lev, uint64_t n,
+                               const double *ip0, const double *ip1, unsigned flags)
+{
+  DA *da = new DA;
+  da->dim = dim; da->order = order; da->max_depth = max_depth; da->sfc_mode = sfc;
+  da->M = order + 1;
+  da->N = 1;
+  for (int i = 0; i < dim; i++) da->N *= da->M;
+  for (int i = 0; i < da->M * da->M; i++) { da->ip[0][i] = ip0[i]; da->ip[1][i] = ip1[i]; }
+  int rc = build_da(*da, xyz, lev, n, flags);
+  if (rc == DKT_OK) rc = build_chunks(*da);
+  if (rc != DKT_OK)
+  {
+    const std::string keep = g_err;
+    free_da(*da);
+    delete da;
+    g_err = keep;
+    return nullptr;
+  }
+  return da;
+}
+extern "C" void emu_da_sizes(void *h, uint64_t *out)
+{
+  const DA &d = *(DA *)h;
+  out[0] = d.nElem; out[1] = d.nMv; out[2] = d.nReg; out[3] = d.nHang; out[4] = d.nNodes; out[5] = d.nBdy; out[6] = d.nSplit;
+  out[7] = (uint64_t)d.tree_class; out[8] = (uint64_t)d.N; out[9] = (uint64_t)d.finest_level; out[10] = d.sets.size();
+}
+template <typename T>
+static void cp(T *dst, const T *src, size_t n)
+{
+  if (dst && src && n) memcpy(dst, src, n * sizeof(T));
+}
+extern "C" void emu_da_export(void *h, uint32_t *elem_xyz, uint8_t *elem_lev, uint32_t *node_xyz, uint8_t *node_lev, uint32_t *bdy,
+                              uint32_t *mv_xyz, uint8_t *mv_lev, uint32_t *e2n, uint32_t *pnode, uint8_t *child)
+{
+  const DA &d = *(DA *)h;
+  cp(elem_xyz, d.d_elem_xyz, d.nElem * d.dim); cp(elem_lev, d.d_elem_lev, d.nElem);
+  cp(node_xyz, d.d_node_xyz, d.nNodes * d.dim); cp(node_lev, d.d_node_lev, d.nNodes);
+  cp(bdy, d.d_bdy, d.nBdy);
+  cp(mv_xyz, d.d_mv_xyz, d.nMv * d.dim); cp(mv_lev, d.d_mv_lev, d.nMv);
+  cp(e2n, d.d_e2n, d.nMv * d.N); cp(pnode, d.d_pnode, d.nHang * d.N); cp(child, d.d_child, d.nHang);
+}
+extern "C" int emu_da_matvec(void *h, int kind, const double *kref, double alpha, int dirichlet, const double *in, double *out, double scale,
+                             unsigned flags)
+{
+  DA &d = *(DA *)h;
+  dkt_op op;
+  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  double *din = nullptr, *dout = nullptr;
+  cudaMalloc(&din, d.nNodes * sizeof(double));
+  cudaMalloc(&dout, d.nNodes * sizeof(double));
+  memcpy(din, in, d.nNodes * sizeof(double));
+  const int rc = run_matvec_chunked(d, &op, din, dout, scale, flags);
+  memcpy(out, dout, d.nNodes * sizeof(double));
+  cudaFree(din);
+  cudaFree(dout);
+  return rc;
+}
+extern "C" void emu_da_destroy(void *h)
+{
+  DA *da = (DA *)h;
+  free_da(*da);
+  delete da;
+}

@@ -1,0 +1,90 @@
+"""CPU tests of the PRODUCT's single-rank pipeline under the CUDA-on-CPU emulation (tests/emu): dkt_build.cu (tree order,
+CG node set and order, element->node and hanging tables, phantom elements), dkt_chunks.cu (chunk tables, kernels) and
+dkt_sfc.cpp compiled with g++ and driven like dkt_da_create / dkt_matvec.  Same assertions as the GPU parity test
+(tests/test_gpu_parity.py): construction-time tables bit-exact against the reference's golden fixtures, vectors within
+1e-12.  This checks the library's LOGIC without a GPU; it is not a CPU path of the product (libdkt.so has none)."""
+import numpy as np
+import pytest
+
+import cases
+import emu_full
+import flat
+from test_oracle import load_case
+
+TOL = 1e-12
+INVALID = 0xFFFFFFFF
+GROUP_SPECS = {2: ["2"], 3: ["3", "3,2"], 4: ["2", "2,1"]}
+
+
+def _sorted_rows(xyz, lev, *cols):
+    key = np.lexsort(tuple(xyz[:, d] for d in range(xyz.shape[1])) + (lev,))
+    return [c[key] for c in (xyz, lev) + cols]
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_emulated_pipeline_matches_reference(name):
+    case = load_case(name)
+    g = case["golden"]
+    dim, order, md = case["dim"], case["order"], case["max_depth"]
+    sfc = 1 if case["sfc"] == "hilbert" else 0
+    da = emu_full.EmuDA(case["xyz"], case["lev"], dim, order, md, sfc=sfc, ip0=g["ip0"], ip1=g["ip1"])
+    e = da.export()
+    # --- construction-time tables: bit-exact against the reference -------------------------------
+    assert np.array_equal(e["elem_xyz"], g["elem_xyz"]) and np.array_equal(e["elem_lev"], g["elem_lev"])
+    assert np.array_equal(e["node_xyz"], g["node_xyz"]), "CG node order differs from DA::getTNCoords()"
+    assert np.array_equal(e["node_lev"], g["node_lev"])
+    assert np.array_equal(e["bdy"], g["bdy"])
+    assert da.n_mv_elem == int(g["ncalls"])
+    # --- flat tables against the oracle ------------------------------------------------------------
+    t = cases.oracle_tables_for(case)
+    assert da.tree_class == t.tree_class
+    oe2n = np.where(t.e2n < 0, INVALID, t.e2n).astype(np.uint32)
+    for x, y in zip(_sorted_rows(e["mv_xyz"], e["mv_lev"], e["e2n"]), _sorted_rows(t.mv_xyz, t.mv_lev, oe2n)):
+        assert np.array_equal(x, y)
+    nh = da.n_hanging
+    assert nh == len(t.hang_idx)
+    if nh:
+        op = np.where(t.pnode < 0, INVALID, t.pnode).astype(np.uint32)
+        a = _sorted_rows(e["mv_xyz"][-nh:], e["mv_lev"][-nh:], e["pnode"], e["child"])
+        b = _sorted_rows(t.mv_xyz[t.hang_idx], t.mv_lev[t.hang_idx], op, t.child.astype(np.uint8))
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # --- matvec against the reference's own output ---------------------------------------------------
+    n = da.n_nodes
+    K = cases.dense_operator(dim, order)
+    u = cases.input_vector(n)
+    assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"])), g["v_dense"]) <= TOL
+    if len(t.mv_lev) < 50000:
+        assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"]), dirichlet=True), g["v_dense_diri"]) <= TOL
+        assert rel(da.matvec(np.ones(n)), g["v_id"]) <= TOL
+    da.close()
+    # --- the same tree with sibling-group chunk tables (opt-in DKT_GROUPS) ----------------------------------
+    if order == 1 and len(t.mv_lev) < 50000:
+        for spec in GROUP_SPECS[dim]:
+            dg = emu_full.EmuDA(case["xyz"], case["lev"], dim, order, md, sfc=sfc, ip0=g["ip0"], ip1=g["ip1"], groups=spec)
+            assert rel(dg.matvec(np.ones(n)), g["v_id"]) <= TOL
+            Kl = flat.laplace_kref(dim, 1)
+            vo = flat.matvec(t, u, Kl, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
+            assert rel(dg.matvec(u, kref=Kl, alpha=dim - 2.0, scale=0.7, dirichlet=True), vo) <= TOL
+            dg.close()
+
+
+def test_emulated_pipeline_refuses_class_u():
+    """the stock moving-ball sphere touches the domain boundary with level jumps: class U"""
+    import dkt
+    dim, md = 4, 8
+    c = np.full(dim, 0.25)
+
+    def g(ctr):
+        return np.abs(np.sqrt(((ctr - c) ** 2).sum(axis=1)) - 0.25) * 1.1
+
+    xyz, lev = dkt.trees._refine(np, dim, md, 1, 4, g)
+    t = flat.build_tables(xyz, lev, dim, 1, md)
+    if t.tree_class != "U":
+        pytest.skip("generator did not produce a class-U tree")
+    with pytest.raises(RuntimeError, match="class-U"):
+        emu_full.EmuDA(xyz, lev, dim, 1, md)
