@@ -16,6 +16,14 @@
 // matrix entry as an immediate constant operand.
 #include "dkt_internal.h"
 
+// also compiles under -DDKT_EMU (tests/emu/cuda_emu.h) for the CPU test-suite; never part of libdkt.so that way
+#ifdef DKT_EMU
+#include "cuda_emu.h"
+#define DKT_FLAT_LAUNCH(kern, grid, stream) ::emu::make_launch_flat(kern, (grid), 128)
+#else
+#define DKT_FLAT_LAUNCH(kern, grid, stream) kern<<<(grid), 128, 0, (stream)>>>
+#endif
+
 #include <cstdio>
 #include <cstring>
 
@@ -229,14 +237,20 @@ static int launch_mv(DA &da, const MvParams<DIM, ORDER> &base)
   {
     p.first = (uint32_t)first;
     p.count = (uint32_t)std::min<uint64_t>(chunk, da.nReg - first);
-    k_mv_regular<DIM, ORDER, OPKIND, DIRI><<<(p.count + 127) / 128, 128, 0, da.stream>>>(p);
+    {
+      auto kern = k_mv_regular<DIM, ORDER, OPKIND, DIRI>;
+      DKT_FLAT_LAUNCH(kern, (p.count + 127) / 128, da.stream)(p);
+    }
     g_launches++;
   }
   if (da.nHang)
   {
     p.first = (uint32_t)da.nReg;
     p.count = (uint32_t)da.nHang;
-    k_mv_hanging<DIM, ORDER, OPKIND, DIRI><<<(p.count + 127) / 128, 128, 0, da.stream>>>(p);
+    {
+      auto kern = k_mv_hanging<DIM, ORDER, OPKIND, DIRI>;
+      DKT_FLAT_LAUNCH(kern, (p.count + 127) / 128, da.stream)(p);
+    }
     g_launches++;
   }
   CK(cudaGetLastError());

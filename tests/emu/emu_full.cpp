@@ -11,11 +11,6 @@ namespace dkt
 static std::string g_err;
 uint64_t g_launches = 0;
 void set_error(const std::string &msg) { g_err = msg; }
-int run_matvec(DA &, const dkt_op *, const double *, double *, double, unsigned)
-{
-  set_error("emulation: flat kernels are not part of the emulated build");
-  return DKT_ERR_UNSUPPORTED;
-}
 void free_dist(Dist &) {}
 }  // namespace dkt
 
@@ -75,7 +70,9 @@ extern "C" int emu_da_matvec(void *h, int kind, const double *kref, double alpha
   cudaMalloc(&din, d.nNodes * sizeof(double));
   cudaMalloc(&dout, d.nNodes * sizeof(double));
   memcpy(din, in, d.nNodes * sizeof(double));
-  const int rc = run_matvec_chunked(d, &op, din, dout, scale, flags);
+  // like dkt_matvec: the Q1-free variant and DKT_MV_FLAT run on the flat kernels
+  if (flags & DKT_NO_Q1_MASK) flags |= DKT_MV_FLAT;
+  const int rc = (flags & DKT_MV_FLAT) ? run_matvec(d, &op, din, dout, scale, flags) : run_matvec_chunked(d, &op, din, dout, scale, flags);
   memcpy(out, dout, d.nNodes * sizeof(double));
   cudaFree(din);
   cudaFree(dout);

@@ -17,7 +17,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(CSRC, "dkt_build.cu"), os.path.join(CSRC, "dkt_chunks.cu"), os.path.join(CSRC, "dkt_sfc.cpp"),
+    srcs = [os.path.join(CSRC, "dkt_build.cu"), os.path.join(CSRC, "dkt_chunks.cu"), os.path.join(CSRC, "dkt_matvec.cu"),
+            os.path.join(CSRC, "dkt_sfc.cpp"),
             os.path.join(EMU, "cuda_emu.cpp"), os.path.join(EMU, "emu_full.cpp")]
     deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(ROOT, "include", "dkt.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
@@ -82,7 +83,8 @@ class EmuDA:
                                                             "e2n", "pnode", "child")])
         return out
 
-    def matvec(self, u, kref=None, alpha=0.0, scale=1.0, dirichlet=False, flags=0):
+    def matvec(self, u, kref=None, alpha=0.0, scale=1.0, dirichlet=False, flags=0, flat=False, q1_mask=True, fastpath=True):
+        flags |= (4 if flat else 0) | (0 if q1_mask else 2) | (0 if fastpath else 8)
         u = np.ascontiguousarray(u, dtype=np.float64)
         kr = None if kref is None else np.ascontiguousarray(np.asarray(kref, dtype=np.float64).ravel())
         out = np.full(self.n_nodes, np.nan)

@@ -61,6 +61,16 @@ def test_emulated_pipeline_matches_reference(name):
     if len(t.mv_lev) < 50000:
         assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"]), dirichlet=True), g["v_dense_diri"]) <= TOL
         assert rel(da.matvec(np.ones(n)), g["v_id"]) <= TOL
+        # the flat kernels (independent second implementation) and the mathematically consistent variant without Q1
+        assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"]), flat=True), g["v_dense"]) <= TOL
+        assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"]), dirichlet=True, flat=True), g["v_dense_diri"]) <= TOL
+        vo2 = flat.matvec(t, u, K, alpha=float(g["alpha"]), scale=float(g["scale"]), ip0=g["ip0"], ip1=g["ip1"], q1_mask=False)
+        assert rel(da.matvec(u, kref=K, alpha=float(g["alpha"]), scale=float(g["scale"]), q1_mask=False), vo2) <= TOL
+        if order == 1:  # Walsh-Hadamard fast path against the dense product of the same operator
+            Kl = flat.laplace_kref(dim, 1)
+            v_fast = da.matvec(u, kref=Kl, alpha=dim - 2.0)
+            v_dense = da.matvec(u, kref=Kl, alpha=dim - 2.0, fastpath=False)
+            assert rel(v_fast, v_dense) <= TOL
     da.close()
     # --- the same tree with sibling-group chunk tables (opt-in DKT_GROUPS) ----------------------------------
     if order == 1 and len(t.mv_lev) < 50000:
