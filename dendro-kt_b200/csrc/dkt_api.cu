@@ -117,7 +117,6 @@ extern "C"
     *out = nullptr;
     if (dim < 2 || dim > 4) { set_error("dim must be 2, 3 or 4"); return DKT_ERR_INVALID; }
     if (order < 1 || order > 2) { set_error("order must be 1 or 2 (low-order node resolver, include/nsort.tcc:1267)"); return DKT_ERR_UNSUPPORTED; }
-    if (dim == 4 && order == 2) { set_error("4-D order 2 (81 nodes per element) has no kernel yet"); return DKT_ERR_UNSUPPORTED; }
     if (max_depth < 1 || max_depth > 30) { set_error("max_depth must be in 1..30"); return DKT_ERR_INVALID; }
     if (sfc_mode != DKT_SFC_MORTON && sfc_mode != DKT_SFC_HILBERT) { set_error("bad sfc_mode"); return DKT_ERR_INVALID; }
     if (!elem_xyz || !elem_lev) { set_error("element arrays are NULL"); return DKT_ERR_INVALID; }

@@ -841,6 +841,8 @@ static int groups_requested(const DA &da, int &gH)
 
 int build_chunks(DA &da)
 {
+  // more than 27 nodes per element (4-D order 2): no shared-memory kernel; every matvec runs on the flat kernels
+  if (da.N > MAX_NPE) return DKT_OK;
   if (da.nNodes >= 0x7FFFFFFFull) { set_error("more than 2^31 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
   if (getenv("DKT_GROUPS") && da.nNodes >= 0x3FFFFFFFull) { set_error("DKT_GROUPS: more than 2^30 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
   CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
@@ -2059,6 +2061,7 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
 int run_matvec_chunked(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags, unsigned phaseMask,
                        bool zeroOut)
 {
+  if (da.N > MAX_NPE) return run_matvec(da, op, d_in, d_out, scale, flags);  // 81 nodes per element: flat kernels only
   const int key = da.dim * 10 + da.order;
   switch (key)
   {

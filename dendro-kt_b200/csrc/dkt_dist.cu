@@ -697,6 +697,7 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
   const uint64_t totalSend = d.send_off[d.nranks];
   // DKT_VEC_GHOSTED: the caller's vectors already have room for the ghost segment ([owned | ghosts],
   // like the reference's ghosted vectors) and are used in place - no staging copies
+  if (da.N > MAX_NPE) flags |= DKT_MV_FLAT;  // 81 nodes per element: flat kernels only (no phases)
   const bool ghosted = (flags & DKT_VEC_GHOSTED) != 0;
   double *in_local = ghosted ? const_cast<double *>(d_in) : d.d_in_local;
   double *out_local = ghosted ? d_out : d.d_out_local;

@@ -111,6 +111,7 @@ struct DA
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr};
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
+  double *d_kbuf = nullptr;        // operator matrix of the 81-node (4-D order 2) flat kernels
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

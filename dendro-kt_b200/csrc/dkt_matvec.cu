@@ -257,6 +257,158 @@ static int launch_mv(DA &da, const MvParams<DIM, ORDER> &base)
   return DKT_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// 81 nodes per element (4-D, order 2): the same algorithm with run-time loops over arrays in local memory and the
+// operator matrix read from device memory (it does not fit the kernel parameter space).  Coverage, not speed: this
+// combination has no shared-memory kernel yet.
+// ------------------------------------------------------------------------------------------
+struct MvBigParams
+{
+  const double *in;
+  double *out;
+  const uint32_t *e2n;
+  const uint8_t *lev;
+  const uint32_t *pnode;
+  const uint8_t *child;
+  const uint8_t *isbdy;
+  const double *K;  // device, N*N row-major, or nullptr for the identity
+  uint32_t first, count;
+  int q1mask, dirichlet;
+  double lscale[32];
+  double ip[2][MAX_M * MAX_M];
+};
+template <int DIM, int M>
+__device__ void interp_big(const double (&ip)[2][MAX_M * MAX_M], int child, bool transpose, double *v)
+{
+  constexpr int N = (DIM == 2 ? M * M : DIM == 3 ? M * M * M : M * M * M * M);
+  int stride = 1;
+  for (int d = 0; d < DIM; d++)
+  {
+    const double *A = ip[(child >> d) & 1];
+    for (int base = 0; base < N; base++)
+    {
+      if ((base / stride) % M != 0) continue;
+      double line[M], res[M];
+      for (int k = 0; k < M; k++) line[k] = v[base + k * stride];
+      for (int j = 0; j < M; j++)
+      {
+        double acc = 0.0;
+        for (int k = 0; k < M; k++) acc = fma(transpose ? A[j * M + k] : A[k * M + j], line[k], acc);
+        res[j] = acc;
+      }
+      for (int j = 0; j < M; j++) v[base + j * stride] = res[j];
+    }
+    stride *= M;
+  }
+}
+template <int DIM, int ORDER, bool HANG>
+__global__ void __launch_bounds__(128) k_mv_big(const __grid_constant__ MvBigParams p)
+{
+  constexpr int M = ORDER + 1;
+  constexpr int N = (DIM == 2 ? M * M : DIM == 3 ? M * M * M : M * M * M * M);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.count) return;
+  const uint64_t e = (uint64_t)p.first + t;
+  const uint32_t *idx = p.e2n + e * N;
+  const uint32_t *pn = HANG ? p.pnode + (uint64_t)t * N : nullptr;
+  const int child = HANG ? p.child[t] : 0;
+  const bool diri = p.dirichlet != 0;
+  double ein[N], eout[N];
+  if (HANG)
+  {
+    for (int r = 0; r < N; r++)
+    {
+      double v = 0.0;
+      if (pn[r] != INVALID)
+      {
+        v = p.in[pn[r]];
+        if (diri && p.isbdy[pn[r]]) v = 0.0;
+      }
+      ein[r] = v;
+    }
+    interp_big<DIM, M>(p.ip, child, false, ein);
+  }
+  for (int r = 0; r < N; r++)
+  {
+    if (idx[r] == INVALID) continue;  // hanging: keep the interpolated value
+    double v = p.in[idx[r]];
+    if (diri && p.isbdy[idx[r]]) v = 0.0;
+    ein[r] = v;
+  }
+  if (!p.K)
+    for (int i = 0; i < N; i++) eout[i] = ein[i];
+  else
+  {
+    const double s = p.lscale[p.lev[e]];
+    for (int i = 0; i < N; i++)
+    {
+      double acc = 0.0;
+      for (int j = 0; j < N; j++) acc = fma(p.K[i * N + j], ein[j], acc);
+      eout[i] = s * acc;
+    }
+  }
+  for (int r = 0; r < N; r++)
+  {
+    if (idx[r] == INVALID) continue;
+    if (!(diri && p.isbdy[idx[r]])) red_add(p.out + idx[r], eout[r]);
+    eout[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
+  }
+  if (HANG)
+  {
+    interp_big<DIM, M>(p.ip, child, true, eout);
+    for (int q = 0; q < N; q++)
+    {
+      if (pn[q] == INVALID) continue;
+      if (p.q1mask && idx[q] != INVALID) continue;  // Q1 (matvec.h:517)
+      if (diri && p.isbdy[pn[q]]) continue;
+      red_add(p.out + pn[q], eout[q]);
+    }
+  }
+}
+template <int DIM, int ORDER>
+static int run_big(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
+{
+  constexpr int M = ORDER + 1;
+  constexpr int N = (DIM == 2 ? M * M : DIM == 3 ? M * M * M : M * M * M * M);
+  MvBigParams p;
+  p.in = d_in; p.out = d_out; p.e2n = da.d_e2n; p.lev = da.d_mv_lev; p.pnode = da.d_pnode; p.child = da.d_child; p.isbdy = da.d_node_isbdy;
+  p.K = nullptr;
+  p.q1mask = (flags & DKT_NO_Q1_MASK) ? 0 : 1;
+  p.dirichlet = op->dirichlet != 0;
+  for (int l = 0; l < 32; l++) p.lscale[l] = scale * std::pow(2.0, -op->alpha * l);
+  for (int b = 0; b < 2; b++)
+    for (int i = 0; i < M * M; i++) p.ip[b][i] = da.ip[b][i];
+  if (op->kind == DKT_OP_DENSE)
+  {
+    if (!op->kref) { set_error("DKT_OP_DENSE needs kref"); return DKT_ERR_INVALID; }
+    if (!da.d_kbuf) CK(cudaMalloc((void **)&da.d_kbuf, sizeof(double) * N * N));
+    CK(cudaMemcpyAsync(da.d_kbuf, op->kref, sizeof(double) * N * N, cudaMemcpyHostToDevice, da.stream));
+    CK(cudaStreamSynchronize(da.stream));  // kref is the caller's pageable memory
+    p.K = da.d_kbuf;
+  }
+  else if (op->kind != DKT_OP_IDENTITY) { set_error("unknown operator kind"); return DKT_ERR_INVALID; }
+  CK(cudaMemsetAsync(d_out, 0, da.nNodes * sizeof(double), da.stream));
+  g_launches++;
+  if (da.nReg)
+  {
+    p.first = 0;
+    p.count = (uint32_t)da.nReg;
+    auto kern = k_mv_big<DIM, ORDER, false>;
+    DKT_FLAT_LAUNCH(kern, (p.count + 127) / 128, da.stream)(p);
+    g_launches++;
+  }
+  if (da.nHang)
+  {
+    p.first = (uint32_t)da.nReg;
+    p.count = (uint32_t)da.nHang;
+    auto kern = k_mv_big<DIM, ORDER, true>;
+    DKT_FLAT_LAUNCH(kern, (p.count + 127) / 128, da.stream)(p);
+    g_launches++;
+  }
+  CK(cudaGetLastError());
+  return DKT_OK;
+}
+
 template <int DIM, int ORDER>
 static int run_typed(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
 {
@@ -299,8 +451,9 @@ int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, doub
   case 31: return run_typed<3, 1>(da, op, d_in, d_out, scale, flags);
   case 32: return run_typed<3, 2>(da, op, d_in, d_out, scale, flags);
   case 41: return run_typed<4, 1>(da, op, d_in, d_out, scale, flags);
+  case 42: return run_big<4, 2>(da, op, d_in, d_out, scale, flags);
   default:
-    set_error("unsupported (dim, order): kernels exist for dim 2,3 with order 1,2 and dim 4 with order 1");
+    set_error("unsupported (dim, order): kernels exist for dim 2-4 with order 1,2");
     return DKT_ERR_UNSUPPORTED;
   }
 }

@@ -95,6 +95,9 @@ GENERATED_CASES = [
     "ex1-d2-p1-hilbert-5", "ex3-d3-p1-hilbert-3", "ex3-d4-p1-hilbert-3", "ex3-d3-p2-hilbert-3",
 ]
 ALL_CASES = GENERATED_CASES + POINT_CLOUD_CASES
+# 4-D order 2 (81 nodes per element): table construction is the generic one; the matvec runs on the loop-based flat
+# kernels (dkt_matvec.cu k_mv_big).  Checked on the CPU (oracle + emulated pipeline); GPU tests opt-in until confirmed.
+D4P2_CASES = ["ex1-d4-p2-morton-3", "ex1-d4-p2-hilbert-3"]
 
 
 def dense_operator(dim, order, seed=5):

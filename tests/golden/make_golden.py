@@ -102,7 +102,7 @@ def main():
         print("%-28s nN=%6d alpha=%.3f  %6.1f KB" % (fixture, len(g["v_heat"]), g["heat_alpha"], os.path.getsize(path) / 1024))
     if "--heatmat-only" in sys.argv:
         return
-    for name in cases.ALL_CASES:
+    for name in cases.ALL_CASES + cases.D4P2_CASES:
         case = point_cloud_case(name) if name in cases.POINT_CLOUD_CASES else cases.make_case(name)
         g = generate(case)
         path = os.path.join(HERE, name + ".npz")

@@ -25,7 +25,7 @@ def rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
 
-@pytest.mark.parametrize("name", cases.ALL_CASES)
+@pytest.mark.parametrize("name", cases.ALL_CASES + cases.D4P2_CASES)
 def test_emulated_pipeline_matches_reference(name):
     case = load_case(name)
     g = case["golden"]

@@ -19,7 +19,7 @@ def load_case(name):
     return case
 
 
-@pytest.mark.parametrize("name", cases.ALL_CASES)
+@pytest.mark.parametrize("name", cases.ALL_CASES + cases.D4P2_CASES)
 def test_oracle_matches_golden(name):
     case = load_case(name)
     g = case["golden"]

@@ -8,6 +8,8 @@ mkdir -p $out
 python __graft_entry__.py > $out/build.log 2>&1
 DKT_TEST_GROUPS=1 timeout 900 python -m pytest tests/test_zz_gpu_groups.py -x -q -m gpu > $out/pytest_groups.log 2>&1
 echo "pytest groups rc=$?" | tee -a $out/summary.txt
+DKT_TEST_D4P2=1 timeout 300 python -m pytest tests/test_zz_gpu_d4p2.py -x -q -m gpu > $out/pytest_d4p2.log 2>&1
+echo "pytest d4p2 rc=$?" | tee -a $out/summary.txt
 # the peer-memory exchange protocol with all ranks of a partition in one process on this one GPU
 DKT_TEST_P2P=1 timeout 600 python -m pytest tests/test_zz_gpu_p2p_local.py -x -q -m gpu > $out/pytest_p2p_local.log 2>&1
 echo "pytest p2p local rc=$?" | tee -a $out/summary.txt
