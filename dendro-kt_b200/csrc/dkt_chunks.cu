@@ -1981,7 +1981,7 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
                       bool zeroOut)
 {
   using P = Mv3Params<DIM, ORDER>;
-  static P p;
+  static thread_local P p;  // large; per host thread, so that independent DAs may be driven from different threads
   p.in = d_in;
   p.out = d_out;
   p.q1mask = (flags & DKT_NO_Q1_MASK) ? 0 : 1;
@@ -2011,7 +2011,7 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
     {
       // D = H K H / N ; if it is diagonal the operator is applied in Walsh-Hadamard form
       constexpr int N = P::N;
-      static double T[N * N], D[N * N];
+      static thread_local double T[N * N], D[N * N];
       auto h = [](int i, int j) { return (__builtin_popcount((unsigned)(i & j)) & 1) ? -1.0 : 1.0; };
       for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++)

@@ -413,7 +413,7 @@ template <int DIM, int ORDER>
 static int run_typed(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
 {
   using P = MvParams<DIM, ORDER>;
-  static P p;  // large (K up to 27x27); filled per call, copied into the launch
+  static thread_local P p;  // large (K up to 27x27); filled per call, copied into the launch; per host thread
   p.in = d_in;
   p.out = d_out;
   p.e2n = da.d_e2n;
