@@ -1455,6 +1455,7 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
   p.xcap = (uint32_t)rows_per_chunk(N) * N + 258u;  // + padding of the first 16 diagonals + the trash position
   p.ncap = (cs.maxNloc + 2) & ~1u;
   p.jdStride = cs.jdStride;
+  if (cs.maxNloc > (uint32_t)(NPT * TPB)) { set_error("internal: more nodes in a chunk than its kernel handles"); return DKT_ERR_UNSUPPORTED; }
   const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.jdStride * sizeof(int);
   auto kern = k_mv3<DIM, ORDER, OPKIND, DIRI, HANG, TPB, NPT, EXIP>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1929,6 +1930,9 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
   constexpr int TPB_R = (N == 27) ? 160 : DKT_ROWS;  // >= elements per chunk (one element per thread)
   constexpr int TPB_H = (N == 27) ? 96 : DKT_ROWS / 2;
   constexpr bool CAN_EXIP = (ORDER == 1 && OPKIND != DKT_OP_DENSE);
+  // nodes per thread of the fall-back instantiations: enough for a chunk whose slots all touch different nodes
+  // (scattered boundary elements of a partitioned DA at order 2: up to 150 x 27 nodes)
+  constexpr int NPT_R = (SLOT_CAP + TPB_R - 1) / TPB_R, NPT_H = (SLOT_CAP + TPB_H - 1) / TPB_H;
   const bool exip = CAN_EXIP && p.exact_ip;
   // DKT_MV_STREAMS=n (opt-in): the sets of one call are independent (nodes shared between sets are accumulated with
   // RED), so they may run side by side on n streams - small sets then fill the tails of the big ones
@@ -1955,14 +1959,14 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
     else if (cs.rows == 1)
     {
       if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p);
-      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 16, false>(da, cs, p);
+      else rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, NPT_R, false>(da, cs, p);
     }
     else if (cs.maxNloc <= 8u * TPB_H)
     {
       if (exip) rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, CAN_EXIP>(da, cs, p);
       else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 8, false>(da, cs, p);
     }
-    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, 32, false>(da, cs, p);
+    else rc = launch_one<DIM, ORDER, OPKIND, DIRI, true, TPB_H, NPT_H, false>(da, cs, p);
     da.cur = nullptr;
     if (rc) return rc;
   }

@@ -20,7 +20,14 @@
 #include "dkt_internal.h"
 #include "dkt_p2p.cuh"
 
+// also compiles under -DDKT_EMU (tests/emu/cuda_emu.h): the CPU test-suite runs partition_da and the phased matvec of
+// several ranks in one process; never part of libdkt.so that way
+#ifdef DKT_EMU
+#define DKT_DIST_LAUNCH(kern, grid, block, stream) ::emu::make_launch(kern, (grid), (block), 0)
+#else
 #include <cub/cub.cuh>
+#define DKT_DIST_LAUNCH(kern, grid, block, stream) kern<<<(grid), (block), 0, (stream)>>>
+#endif
 
 #include <dlfcn.h>
 
@@ -64,6 +71,9 @@ constexpr int NCCL_UINT8 = 1;
 
 static int load_nccl()
 {
+#ifdef DKT_EMU
+  return DKT_OK;  // dry-run partitions only
+#endif
   if (g_nccl.lib) return DKT_OK;
   const char *cands[] = {getenv("DKT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char *c : cands)
@@ -250,7 +260,7 @@ __global__ void k_unpack_add(double *v, const uint32_t *idx, uint64_t n, const d
   {                                                                            \
     if ((n) > 0)                                                               \
     {                                                                          \
-      kern<<<(unsigned)(((n) + 255) / 256), 256, 0, stream>>>(__VA_ARGS__);     \
+      DKT_DIST_LAUNCH(kern, (unsigned)(((n) + 255) / 256), 256, stream)(__VA_ARGS__); \
       g_launches++;                                                            \
     }                                                                          \
   } while (0)
@@ -417,7 +427,7 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
     CK(cudaMemcpy(&W, wscan + nMv, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     for (int p = 0; p <= nranks; p++)
     {
-      k_lower_bound64<<<1, 1, 0, g.stream>>>(wscan, nMv + 1, (W * (uint64_t)p) / (uint64_t)nranks, dbound + p);
+      DKT_DIST_LAUNCH(k_lower_bound64, 1, 1, g.stream)(wscan, nMv + 1, (W * (uint64_t)p) / (uint64_t)nranks, dbound + p);
       g_launches++;
     }
     std::vector<uint64_t> hb(nranks + 1);
@@ -509,10 +519,10 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   // ---- my element ranges (regular and hanging lists are each sorted by tree position) ----------------------
   uint64_t *dlb = nullptr, lb[4];
   CK(cudaMalloc((void **)&dlb, 4 * sizeof(uint64_t)));
-  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src, nReg, B.b[rank], dlb + 0);
-  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src, nReg, B.b[rank + 1], dlb + 1);
-  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src + nReg, nHang, B.b[rank], dlb + 2);
-  k_lower_bound<<<1, 1, 0, g.stream>>>(g.d_mv_src + nReg, nHang, B.b[rank + 1], dlb + 3);
+  DKT_DIST_LAUNCH(k_lower_bound, 1, 1, g.stream)(g.d_mv_src, nReg, B.b[rank], dlb + 0);
+  DKT_DIST_LAUNCH(k_lower_bound, 1, 1, g.stream)(g.d_mv_src, nReg, B.b[rank + 1], dlb + 1);
+  DKT_DIST_LAUNCH(k_lower_bound, 1, 1, g.stream)(g.d_mv_src + nReg, nHang, B.b[rank], dlb + 2);
+  DKT_DIST_LAUNCH(k_lower_bound, 1, 1, g.stream)(g.d_mv_src + nReg, nHang, B.b[rank + 1], dlb + 3);
   g_launches += 4;
   CK(cudaMemcpyAsync(lb, dlb, sizeof(lb), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
@@ -655,7 +665,7 @@ static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *
   const volatile uint32_t *flagR = (const volatile uint32_t *)d.xbuf, *flagW = flagR + P2P_MAX_RANKS;
   // readFromGhost: owned values other ranks ghost -> their xr, then publish the epoch
   LAUNCHS(k_p2p_put, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
-  k_p2p_signal<<<1, P2P_MAX_RANKS, 0, s>>>(d.d_peer_flagR, d.d_send_off, R, epoch);
+  DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagR, d.d_send_off, R, epoch);
   g_launches++;
   int rc = DKT_OK;
   if (overlap)
@@ -670,7 +680,7 @@ static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *
   if (rc) return rc;
   // writeToGhosts: ghost partial sums -> the owners' xw, publish, then add what came back for the owned nodes
   LAUNCHS(k_p2p_put, nGhost, s, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
-  k_p2p_signal<<<1, P2P_MAX_RANKS, 0, s>>>(d.d_peer_flagW, d.d_recv_off, R, epoch);
+  DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagW, d.d_recv_off, R, epoch);
   g_launches++;
   if (overlap)
   {

@@ -137,6 +137,7 @@ inline void __syncthreads() { emu::yield(); }
 
 template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
@@ -182,6 +183,13 @@ inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d,
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = (cudaStream_t)(void *)0x1; return cudaSuccess; }
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+template <typename H> inline cudaError_t cudaIpcGetMemHandle(H *, void *) { return 2; }
+template <typename H> inline cudaError_t cudaIpcOpenMemHandle(void **, H, unsigned) { return 2; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 template <typename S> inline cudaError_t cudaMemcpyToSymbol(S &sym, const void *src, size_t n) { memcpy(&sym, src, n); return cudaSuccess; }
 #ifndef DKT_INTERNAL_H
 typedef struct CUevent_st *cudaEvent_t;

@@ -1,0 +1,115 @@
+// Several ranks of a partitioned DA in one process under the CUDA-on-CPU emulation (tests only): every rank runs the
+// library's own build_da + partition_da (dry run) + build_chunks, then the harness performs the ghost read / write-back
+// with the library's send and receive lists (what ncclSend/Recv or the peer-memory kernels do between GPUs) around the
+// library's phased chunk matvec.  Checks ownership, local numbering, exchange lists, the [interior | boundary] element
+// order and the phased chunk sets (per-element and sibling-group) on REAL partitions.
+#include "dkt_internal.h"
+#include "cuda_emu.h"
+
+#include <memory>
+#include <string>
+
+namespace dkt
+{
+static std::string g_err;
+uint64_t g_launches = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+int cg_solve(DA &, Dist *, const dkt_op *, double *, const double *, int, double *, double, unsigned, int *, int *) { return DKT_ERR_UNSUPPORTED; }
+}  // namespace dkt
+using namespace dkt;
+
+extern "C" const char *emu_dist_error() { return g_err.c_str(); }
+
+struct Rank
+{
+  DA da;
+  Dist dist;
+  std::vector<double> in, out;
+};
+
+// u, v: vectors in the single-rank DA order (n_global entries).  info[r*8..]: nOwned, nGhost, nMv, nHang, nRegInterior,
+// nHangInterior, phased, number of chunk sets.
+extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const uint32_t *xyz, const uint8_t *lev, uint64_t n,
+                               const double *ip0, const double *ip1, int R, int op_kind, const double *kref, double alpha, int dirichlet,
+                               double scale, const double *u, double *v, uint64_t n_global, uint64_t *info)
+{
+  std::vector<std::unique_ptr<Rank>> ranks;
+  int rc = DKT_OK;
+  for (int r = 0; r < R && rc == DKT_OK; r++)
+  {
+    ranks.emplace_back(new Rank);
+    DA &da = ranks.back()->da;
+    da.dim = dim; da.order = order; da.max_depth = max_depth; da.sfc_mode = sfc;
+    da.M = order + 1;
+    da.N = 1;
+    for (int i = 0; i < dim; i++) da.N *= da.M;
+    for (int i = 0; i < da.M * da.M; i++) { da.ip[0][i] = ip0[i]; da.ip[1][i] = ip1[i]; }
+    rc = build_da(da, xyz, lev, n, 0);
+    if (rc == DKT_OK && da.nNodes != n_global) { set_error("node count differs from the caller's"); rc = DKT_ERR_INVALID; }
+    if (rc == DKT_OK) rc = partition_da(da, ranks.back()->dist, r, R, nullptr);
+    if (rc == DKT_OK) rc = build_chunks(da);
+  }
+  dkt_op op;
+  op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  if (rc == DKT_OK)
+  {
+    // owned values in, ghost read with the send / receive lists
+    for (int r = 0; r < R; r++)
+    {
+      Rank &me = *ranks[r];
+      me.in.assign(me.da.nNodes, std::nan(""));
+      me.out.assign(me.da.nNodes, std::nan(""));
+      for (uint64_t j = 0; j < me.dist.nOwned; j++) me.in[j] = u[me.dist.d_owned_gid[j]];
+      uint64_t *o = info + 8 * r;
+      o[0] = me.dist.nOwned; o[1] = me.dist.nGhost; o[2] = me.da.nMv; o[3] = me.da.nHang; o[4] = me.da.nRegInterior; o[5] = me.da.nHangInterior;
+      o[6] = me.da.phased ? 1 : 0; o[7] = me.da.sets.size();
+    }
+    for (int r = 0; r < R; r++)
+      for (int p = 0; p < R; p++)
+      {
+        if (p == r) continue;
+        Rank &src = *ranks[r], &dst = *ranks[p];
+        const uint64_t a = src.dist.send_off[p], b = src.dist.send_off[p + 1];
+        if (b - a != dst.dist.recv_off[r + 1] - dst.dist.recv_off[r]) { set_error("send and receive counts disagree"); rc = DKT_ERR_INVALID; }
+        for (uint64_t i = a; i < b && rc == DKT_OK; i++)
+          dst.in[dst.dist.nOwned + dst.dist.recv_off[r] + (i - a)] = src.in[src.dist.d_send_idx[i]];
+      }
+  }
+  for (int r = 0; r < R && rc == DKT_OK; r++)
+  {
+    Rank &me = *ranks[r];
+    double *din = nullptr, *dout = nullptr;
+    cudaMalloc(&din, me.da.nNodes * sizeof(double));
+    cudaMalloc(&dout, me.da.nNodes * sizeof(double));
+    memcpy(din, me.in.data(), me.da.nNodes * sizeof(double));
+    if (!me.da.phased) rc = run_matvec_chunked(me.da, &op, din, dout, scale, 0);
+    else
+      for (int ph = 0; ph < 3 && rc == DKT_OK; ph++) rc = run_matvec_chunked(me.da, &op, din, dout, scale, 0, 1u << ph, ph == 0);
+    memcpy(me.out.data(), dout, me.da.nNodes * sizeof(double));
+    cudaFree(din);
+    cudaFree(dout);
+  }
+  if (rc == DKT_OK)
+  {
+    // ghost partial sums back to the owners, accumulated; then gather the owned entries
+    for (int p = 0; p < R; p++)
+      for (int r = 0; r < R; r++)
+      {
+        if (p == r) continue;
+        Rank &gh = *ranks[p], &own = *ranks[r];
+        const uint64_t a = gh.dist.recv_off[r], b = gh.dist.recv_off[r + 1];
+        for (uint64_t i = a; i < b; i++) own.out[own.dist.d_send_idx[own.dist.send_off[p] + (i - a)]] += gh.out[gh.dist.nOwned + i];
+      }
+    for (uint64_t i = 0; i < n_global; i++) v[i] = std::nan("");
+    for (int r = 0; r < R; r++)
+      for (uint64_t j = 0; j < ranks[r]->dist.nOwned; j++) v[ranks[r]->dist.d_owned_gid[j]] = ranks[r]->out[j];
+  }
+  for (auto &rk : ranks)
+  {
+    const std::string keep = g_err;
+    free_dist(rk->dist);
+    free_da(rk->da);
+    g_err = keep;
+  }
+  return rc;
+}
