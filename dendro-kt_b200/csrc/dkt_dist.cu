@@ -654,39 +654,50 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
 }
 
 // The same protocol over peer memory (DKT_DIST_P2P=1): everything on the DA's stream.
+// `stages` (bit mask) exists for the single-process emulation of several ranks, where a rank cannot wait for a flag
+// another rank has not yet had the chance to raise: 1 = put + signal (+ first interior half), 2 = wait for the ghost
+// values, boundary (or all) elements, write-back put + signal (+ second interior half), 4 = wait + accumulate.
 static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double *in_local, double *out_local,
-                               double scale, unsigned flags, bool overlap, bool ghosted)
+                               double scale, unsigned flags, bool overlap, bool ghosted, unsigned stages = 7u)
 {
   cudaStream_t s = da.stream;
   const int R = d.nranks;
   const uint64_t nOwned = d.nOwned, totalSend = d.send_off[R], nGhost = d.recv_off[R];
-  const uint32_t epoch = ++d.epoch;
+  if (stages & 1u) ++d.epoch;
+  const uint32_t epoch = d.epoch;
   double *xr = (double *)(d.xbuf + P2P_FLAG_BYTES), *xw = xr + nGhost;
   const volatile uint32_t *flagR = (const volatile uint32_t *)d.xbuf, *flagW = flagR + P2P_MAX_RANKS;
-  // readFromGhost: owned values other ranks ghost -> their xr, then publish the epoch
-  LAUNCHS(k_p2p_put, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
-  DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagR, d.d_send_off, R, epoch);
-  g_launches++;
   int rc = DKT_OK;
-  if (overlap)
+  if (stages & 1u)
   {
-    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);  // interior, first half
-    if (rc) return rc;
+    // readFromGhost: owned values other ranks ghost -> their xr, then publish the epoch
+    LAUNCHS(k_p2p_put, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
+    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagR, d.d_send_off, R, epoch);
+    g_launches++;
+    if (overlap)
+    {
+      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);  // interior, first half
+      if (rc) return rc;
+    }
   }
-  LAUNCHS(k_p2p_wait_copy, nGhost, s, flagR, d.d_recv_off, R, epoch, xr, in_local + nOwned, nGhost, d.d_p2p_err);
-  if (overlap) rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
-  else rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
-                                  : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
-  if (rc) return rc;
-  // writeToGhosts: ghost partial sums -> the owners' xw, publish, then add what came back for the owned nodes
-  LAUNCHS(k_p2p_put, nGhost, s, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
-  DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagW, d.d_recv_off, R, epoch);
-  g_launches++;
-  if (overlap)
+  if (stages & 2u)
   {
-    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);  // interior, second half
+    LAUNCHS(k_p2p_wait_copy, nGhost, s, flagR, d.d_recv_off, R, epoch, xr, in_local + nOwned, nGhost, d.d_p2p_err);
+    if (overlap) rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
+    else rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
+                                    : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
     if (rc) return rc;
+    // writeToGhosts: ghost partial sums -> the owners' xw, publish, then add what came back for the owned nodes
+    LAUNCHS(k_p2p_put, nGhost, s, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
+    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagW, d.d_recv_off, R, epoch);
+    g_launches++;
+    if (overlap)
+    {
+      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);  // interior, second half
+      if (rc) return rc;
+    }
   }
+  if (!(stages & 4u)) return DKT_OK;
   LAUNCHS(k_p2p_wait_add, totalSend, s, flagW, d.d_send_off, R, epoch, xw, out_local, d.d_send_idx, totalSend, d.d_p2p_err);
   if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (getenv("DKT_P2P_CHECK"))
@@ -702,6 +713,11 @@ static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *
 // v = A u on the partition: in/out are DEVICE vectors of the nOwned owned nodes
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
 {
+  return run_matvec_dist_stages(da, d, op, d_in, d_out, scale, flags, 7u);
+}
+int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags,
+                           unsigned stages)
+{
   cudaStream_t s = da.stream;
   const uint64_t nOwned = d.nOwned;
   const uint64_t totalSend = d.send_off[d.nranks];
@@ -711,9 +727,10 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
   const bool ghosted = (flags & DKT_VEC_GHOSTED) != 0;
   double *in_local = ghosted ? const_cast<double *>(d_in) : d.d_in_local;
   double *out_local = ghosted ? d_out : d.d_out_local;
-  if (!ghosted) CK(cudaMemcpyAsync(in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (!ghosted && (stages & 1u)) CK(cudaMemcpyAsync(in_local, d_in, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   const bool overlap = d.nranks > 1 && da.phased && !(flags & DKT_MV_FLAT);
-  if (d.p2p && d.nranks > 1) return run_matvec_dist_p2p(da, d, op, d_in, d_out, in_local, out_local, scale, flags, overlap, ghosted);
+  if (d.p2p && d.nranks > 1) return run_matvec_dist_p2p(da, d, op, d_in, d_out, in_local, out_local, scale, flags, overlap, ghosted, stages);
+  if (stages != 7u) { set_error("staged execution exists for the peer-memory exchange only"); return DKT_ERR_INVALID; }
   cudaStream_t cs = overlap ? d.comm_stream : s;  // the exchanges run beside the interior elements
   if (d.nranks > 1)
   {

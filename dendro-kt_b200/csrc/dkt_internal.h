@@ -145,6 +145,9 @@ struct Dist
 };
 int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id);
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
+// the same in stages (bit mask, see run_matvec_dist_p2p): only for the single-process emulation of several ranks
+int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags,
+                           unsigned stages);
 void free_dist(Dist &d);
 int nccl_unique_id(void *out128);
 int p2p_attach_local(Dist **ranks, int R);

@@ -31,7 +31,7 @@ struct Rank
 // nHangInterior, phased, number of chunk sets.
 extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const uint32_t *xyz, const uint8_t *lev, uint64_t n,
                                const double *ip0, const double *ip1, int R, int op_kind, const double *kref, double alpha, int dirichlet,
-                               double scale, const double *u, double *v, uint64_t n_global, uint64_t *info)
+                               double scale, const double *u, double *v, uint64_t n_global, uint64_t *info, int p2p)
 {
   std::vector<std::unique_ptr<Rank>> ranks;
   int rc = DKT_OK;
@@ -51,7 +51,43 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
   }
   dkt_op op;
   op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
-  if (rc == DKT_OK)
+  if (rc == DKT_OK && p2p)
+  {
+    // the library's own peer-memory flow (run_matvec_dist_p2p), stage by stage over all ranks, twice (buffer re-use)
+    std::vector<Dist *> dd;
+    for (auto &rk : ranks) dd.push_back(&rk->dist);
+    rc = p2p_attach_local(dd.data(), R);
+    std::vector<double *> din(R, nullptr), dout(R, nullptr);
+    for (int r = 0; r < R && rc == DKT_OK; r++)
+    {
+      Rank &me = *ranks[r];
+      cudaMalloc(&din[r], std::max<uint64_t>(me.dist.nOwned, 1) * sizeof(double));
+      cudaMalloc(&dout[r], std::max<uint64_t>(me.dist.nOwned, 1) * sizeof(double));
+      uint64_t *o = info + 8 * r;
+      o[0] = me.dist.nOwned; o[1] = me.dist.nGhost; o[2] = me.da.nMv; o[3] = me.da.nHang; o[4] = me.da.nRegInterior; o[5] = me.da.nHangInterior;
+      o[6] = me.da.phased ? 1 : 0; o[7] = me.da.sets.size();
+    }
+    for (int epoch = 0; epoch < 2 && rc == DKT_OK; epoch++)
+    {
+      for (int r = 0; r < R; r++)
+        for (uint64_t j = 0; j < ranks[r]->dist.nOwned; j++) din[r][j] = (epoch == 0 ? 0.5 : 1.0) * u[ranks[r]->dist.d_owned_gid[j]];
+      for (unsigned stage = 1; stage <= 4 && rc == DKT_OK; stage <<= 1)
+        for (int r = 0; r < R && rc == DKT_OK; r++)
+          rc = run_matvec_dist_stages(ranks[r]->da, ranks[r]->dist, &op, din[r], dout[r], scale, DKT_VEC_DEVICE, stage);
+    }
+    if (rc == DKT_OK)
+    {
+      for (uint64_t i = 0; i < n_global; i++) v[i] = std::nan("");
+      for (int r = 0; r < R; r++)
+      {
+        for (uint64_t j = 0; j < ranks[r]->dist.nOwned; j++) v[ranks[r]->dist.d_owned_gid[j]] = dout[r][j];
+        int err = *ranks[r]->dist.d_p2p_err;
+        if (err) { set_error("a peer-memory wait timed out"); rc = DKT_ERR_NCCL; }
+      }
+    }
+    for (int r = 0; r < R; r++) { cudaFree(din[r]); cudaFree(dout[r]); }
+  }
+  else if (rc == DKT_OK)
   {
     // owned values in, ghost read with the send / receive lists
     for (int r = 0; r < R; r++)
@@ -75,7 +111,7 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
           dst.in[dst.dist.nOwned + dst.dist.recv_off[r] + (i - a)] = src.in[src.dist.d_send_idx[i]];
       }
   }
-  for (int r = 0; r < R && rc == DKT_OK; r++)
+  for (int r = 0; r < R && rc == DKT_OK && !p2p; r++)
   {
     Rank &me = *ranks[r];
     double *din = nullptr, *dout = nullptr;
@@ -89,7 +125,7 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
     cudaFree(din);
     cudaFree(dout);
   }
-  if (rc == DKT_OK)
+  if (rc == DKT_OK && !p2p)
   {
     // ghost partial sums back to the owners, accumulated; then gather the owned entries
     for (int p = 0; p < R; p++)

@@ -1,7 +1,7 @@
 """CPU test of the multi-rank path under the CUDA-on-CPU emulation (tests/emu/emu_dist.cpp): every rank runs the library's
 own build_da + partition_da (dry run) + build_chunks in one process; the harness moves the ghost values with the
-library's send / receive lists around the library's (phased) chunk matvec; the gathered result must equal the
-single-rank vector of the oracle.  Covers ownership, local numbering, exchange lists, the [interior | boundary] element
+library's send / receive lists around the library's (phased) chunk matvec - or (p2p=1) the library's own peer-memory flow run_matvec_dist_p2p runs stage by
+stage over all ranks, twice; the gathered result must equal the single-rank vector of the oracle.  Covers ownership, local numbering, exchange lists, the [interior | boundary] element
 order with comm/compute phases, and the sibling-group tables on real partitions - without GPUs or NCCL."""
 import ctypes as C
 import os
@@ -34,17 +34,18 @@ def _lib():
     L.emu_dist_error.restype = C.c_char_p
     L.emu_dist_matvec.restype = C.c_int
     L.emu_dist_matvec.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                  C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+                                  C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     return L
 
 
+@pytest.mark.parametrize("p2p", [0, 1])
 @pytest.mark.parametrize("name,R,groups,overlap", [
     ("ball-d2-p1-morton-7", 2, "0", "0"), ("ball-d2-p1-morton-7", 3, "2", "1"),
     ("ball-d3-p1-morton-6", 3, "0", "1"), ("ball-d3-p1-morton-6", 8, "3", "1"), ("ball-d3-p1-morton-6", 2, "3,2", "0"),
     ("gauss-d4-p1-morton", 4, "0", "1"), ("gauss-d4-p1-morton", 3, "2", "1"), ("ex3-d4-p1-hilbert-3", 5, "2,1", "1"),
     ("gauss-d3-p2-morton", 3, "0", "1"),
 ])
-def test_emulated_partitioned_matvec(name, R, groups, overlap):
+def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
     case = load_case(name)
     g = case["golden"]
     dim, order, md = case["dim"], case["order"], case["max_depth"]
@@ -70,7 +71,7 @@ def test_emulated_partitioned_matvec(name, R, groups, overlap):
     try:
         L = _lib()
         rc = L.emu_dist_matvec(dim, order, md, 1 if case["sfc"] == "hilbert" else 0, p(xyz), p(lev), len(lev), p(ip0), p(ip1), R, 1, p(Kc),
-                               alpha, 1, 0.7, p(u), p(v), n, p(info))
+                               alpha, 1, 0.7, p(u), p(v), n, p(info), p2p)
     finally:
         for k, val in old.items():
             if val is None:
