@@ -38,12 +38,11 @@ def _lib():
     return L
 
 
-@pytest.mark.parametrize("p2p", [0, 1])
-@pytest.mark.parametrize("name,R,groups,overlap", [
-    ("ball-d2-p1-morton-7", 2, "0", "0"), ("ball-d2-p1-morton-7", 3, "2", "1"),
-    ("ball-d3-p1-morton-6", 3, "0", "1"), ("ball-d3-p1-morton-6", 8, "3", "1"), ("ball-d3-p1-morton-6", 2, "3,2", "0"),
-    ("gauss-d4-p1-morton", 4, "0", "1"), ("gauss-d4-p1-morton", 3, "2", "1"), ("ex3-d4-p1-hilbert-3", 5, "2,1", "1"),
-    ("gauss-d3-p2-morton", 3, "0", "1"),
+@pytest.mark.parametrize("name,R,groups,overlap,p2p", [
+    ("ball-d2-p1-morton-7", 2, "0", "0", 0), ("ball-d2-p1-morton-7", 3, "2", "1", 1),
+    ("ball-d3-p1-morton-6", 3, "0", "1", 1), ("ball-d3-p1-morton-6", 8, "3", "1", 0), ("ball-d3-p1-morton-6", 2, "3,2", "0", 1),
+    ("gauss-d4-p1-morton", 4, "0", "1", 0), ("gauss-d4-p1-morton", 3, "2", "1", 1), ("ex3-d4-p1-hilbert-3", 5, "2,1", "1", 0),
+    ("ex3-d4-p1-hilbert-3", 8, "2", "0", 1), ("gauss-d3-p2-morton", 3, "0", "1", 0), ("gauss-d3-p2-morton", 4, "0", "1", 1),
 ])
 def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
     case = load_case(name)
