@@ -31,6 +31,7 @@ void yield()
   }
   s.barriers++;
   Fiber &f = s.fibers[s.current];
+  f.barriers++;
   swapcontext(&f.ctx, &s.sched);
 }
 
@@ -52,6 +53,7 @@ void run_block(unsigned nthreads, const std::function<void()> &body)
     Fiber &f = s.fibers[t];
     if (!f.stack) f.stack = (char *)malloc(STACK);
     f.done = false;
+    f.barriers = 0;
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack;
     f.ctx.uc_stack.ss_size = STACK;
@@ -76,5 +78,13 @@ void run_block(unsigned nthreads, const std::function<void()> &body)
     }
   }
   s.current = -1;
+  // every thread of a block must pass the same barriers (a divergent __syncthreads() hangs a real GPU)
+  for (unsigned t = 1; t < nthreads; t++)
+    if (s.fibers[t].barriers != s.fibers[0].barriers)
+    {
+      fprintf(stderr, "emu: threads 0 and %u of block %u executed %lu and %lu barriers\n", t, blockIdx.x, s.fibers[0].barriers,
+              s.fibers[t].barriers);
+      abort();
+    }
 }
 }  // namespace emu

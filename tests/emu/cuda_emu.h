@@ -51,6 +51,7 @@ struct Fiber
   ucontext_t ctx;
   char *stack = nullptr;
   bool done = false;
+  unsigned long barriers = 0;  // __syncthreads() executed by this thread in the current block
 };
 struct State
 {
