@@ -23,7 +23,7 @@ namespace dkt
 // write-back flag of matvec e, which the peer raised after it had consumed the data of matvec e.
 constexpr size_t P2P_FLAG_BYTES = 1024;
 constexpr int P2P_MAX_RANKS = 64;
-__global__ void k_p2p_put(const double *src, const uint32_t *idx, uint64_t n, const uint64_t *seg_off, double *const *peer_dst, int nranks)
+static __global__ void k_p2p_put(const double *src, const uint32_t *idx, uint64_t n, const uint64_t *seg_off, double *const *peer_dst, int nranks)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -32,7 +32,7 @@ __global__ void k_p2p_put(const double *src, const uint32_t *idx, uint64_t n, co
   peer_dst[p][i - seg_off[p]] = idx ? src[idx[i]] : src[i];
   __threadfence_system();
 }
-__global__ void k_p2p_signal(uint32_t *const *peer_flag, const uint64_t *seg_off, int nranks, uint32_t epoch)
+static __global__ void k_p2p_signal(uint32_t *const *peer_flag, const uint64_t *seg_off, int nranks, uint32_t epoch)
 {
   const int p = threadIdx.x;
   if (p >= nranks || seg_off[p + 1] == seg_off[p]) return;  // nothing was sent to p
@@ -55,7 +55,7 @@ __device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const u
   }
   __syncthreads();
 }
-__global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
+static __global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
                                 double *dst, uint64_t n, int *err)
 {
   p2p_wait(flags, seg_off, nranks, epoch, err);
@@ -63,7 +63,7 @@ __global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *
   if (i < n) dst[i] = __ldcg(x + i);
 }
 // several peers may return contributions to the same owned node -> atomic
-__global__ void k_p2p_wait_add(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
+static __global__ void k_p2p_wait_add(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
                                double *v, const uint32_t *idx, uint64_t n, int *err)
 {
   p2p_wait(flags, seg_off, nranks, epoch, err);

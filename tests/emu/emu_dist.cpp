@@ -9,16 +9,10 @@
 #include <memory>
 #include <string>
 
-namespace dkt
-{
-static std::string g_err;
-uint64_t g_launches = 0;
-void set_error(const std::string &msg) { g_err = msg; }
-int cg_solve(DA &, Dist *, const dkt_op *, double *, const double *, int, double *, double, unsigned, int *, int *) { return DKT_ERR_UNSUPPORTED; }
-}  // namespace dkt
+namespace dkt { extern std::string g_emu_err; }
+#define g_err g_emu_err
 using namespace dkt;
 
-extern "C" const char *emu_dist_error() { return g_err.c_str(); }
 
 struct Rank
 {

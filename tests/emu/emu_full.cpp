@@ -6,17 +6,11 @@
 
 #include <string>
 
-namespace dkt
-{
-static std::string g_err;
-uint64_t g_launches = 0;
-void set_error(const std::string &msg) { g_err = msg; }
-void free_dist(Dist &) {}
-}  // namespace dkt
+namespace dkt { extern std::string g_emu_err; }
+#define g_err g_emu_err
 
 using namespace dkt;
 
-extern "C" const char *emu_full_error() { return g_err.c_str(); }
 
 extern "C" void *emu_da_create(int dim, int order, int max_depth, int sfc, const uint32_t *xyz, const uint8_t *lev, uint64_t n,
                                const double *ip0, const double *ip1, unsigned flags)

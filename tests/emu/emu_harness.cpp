@@ -6,29 +6,7 @@
 
 #include <string>
 
-namespace dkt
-{
-static std::string g_err;
-uint64_t g_launches = 0;
-void set_error(const std::string &msg) { g_err = msg; }
-int device_exclusive_scan(DA &, const uint64_t *in, uint64_t *out, uint64_t n)
-{
-  uint64_t acc = 0;
-  for (uint64_t i = 0; i < n; i++)
-  {
-    const uint64_t v = in[i];
-    out[i] = acc;
-    acc += v;
-  }
-  return DKT_OK;
-}
-// the flat kernels are not part of the emulated build
-int run_matvec(DA &, const dkt_op *, const double *, double *, double, unsigned)
-{
-  set_error("emulation: flat fallback requested");
-  return DKT_ERR_UNSUPPORTED;
-}
-}  // namespace dkt
+namespace dkt { extern std::string g_emu_err; }
 
 template <typename T>
 static T *dup(const T *src, size_t n)
@@ -39,7 +17,6 @@ static T *dup(const T *src, size_t n)
   return p;
 }
 
-extern "C" const char *emu_last_error() { return dkt::g_err.c_str(); }
 
 // info: per set 8 numbers {kind, rows, g, units, chunks, units per chunk, max nodes per chunk, total chunk nodes}, up to 8 sets
 extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint64_t nReg, uint64_t nNodes, const uint32_t *e2n,
@@ -90,4 +67,3 @@ extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint6
   cudaFree(da.d_e2n); cudaFree(da.d_pnode); cudaFree(da.d_mv_xyz); cudaFree(da.d_mv_lev); cudaFree(da.d_mv_src); cudaFree(da.d_node_isbdy);
   return rc;
 }
-extern "C" void emu_set_order(int order) { emu::state().order = order; }

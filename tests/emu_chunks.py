@@ -15,15 +15,8 @@ _lib = None
 
 
 def build():
-    srcs = [os.path.join(CSRC, "dkt_chunks.cu"), os.path.join(EMU, "cuda_emu.cpp"), os.path.join(EMU, "emu_harness.cpp")]
-    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(ROOT, "include", "dkt.h")]
-    if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-shared", "-fPIC",
-           "-x", "c++"] + srcs + ["-o", LIB]
-    subprocess.check_call(cmd)
-    return LIB
+    import emu_build
+    return emu_build.build()
 
 
 def lib():

@@ -17,16 +17,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(CSRC, "dkt_build.cu"), os.path.join(CSRC, "dkt_chunks.cu"), os.path.join(CSRC, "dkt_matvec.cu"),
-            os.path.join(CSRC, "dkt_sfc.cpp"),
-            os.path.join(EMU, "cuda_emu.cpp"), os.path.join(EMU, "emu_full.cpp")]
-    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(ROOT, "include", "dkt.h")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-shared",
-                               "-fPIC", "-x", "c++"] + srcs + ["-o", LIB])
-    L = C.CDLL(LIB)
-    L.emu_full_error.restype = C.c_char_p
+    import emu_build
+    L = C.CDLL(emu_build.build())
+    L.emu_last_error.restype = C.c_char_p
     L.emu_da_create.restype = C.c_void_p
     L.emu_da_create.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint]
     L.emu_da_sizes.argtypes = [C.c_void_p, C.c_void_p]
@@ -64,7 +57,7 @@ class EmuDA:
             else:
                 os.environ["DKT_GROUPS"] = old
         if not self._h:
-            raise RuntimeError("emu_da_create: " + L.emu_full_error().decode())
+            raise RuntimeError("emu_da_create: " + L.emu_last_error().decode())
         s = np.zeros(16, dtype=np.uint64)
         L.emu_da_sizes(self._h, _p(s))
         (self.n_elem, self.n_mv_elem, self.n_reg, self.n_hanging, self.n_nodes, self.n_boundary, self.n_split, tc, self.N, self.finest_level,
@@ -90,7 +83,7 @@ class EmuDA:
         out = np.full(self.n_nodes, np.nan)
         rc = lib().emu_da_matvec(self._h, 0 if kr is None else 1, _p(kr), alpha, int(dirichlet), _p(u), _p(out), scale, flags)
         if rc:
-            raise RuntimeError("emu_da_matvec rc=%d: %s" % (rc, lib().emu_full_error().decode()))
+            raise RuntimeError("emu_da_matvec rc=%d: %s" % (rc, lib().emu_last_error().decode()))
         return out
 
     def close(self):

@@ -22,16 +22,9 @@ TOL = 1e-12
 
 
 def _lib():
-    srcs = [os.path.join(CSRC, f) for f in ("dkt_build.cu", "dkt_chunks.cu", "dkt_matvec.cu", "dkt_dist.cu", "dkt_sfc.cpp")] + \
-           [os.path.join(EMU, "cuda_emu.cpp"), os.path.join(EMU, "emu_dist.cpp")]
-    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(CSRC, "dkt_p2p.cuh"),
-                   os.path.join(ROOT, "include", "dkt.h")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-shared",
-                               "-fPIC", "-x", "c++"] + srcs + ["-o", LIB])
-    L = C.CDLL(LIB)
-    L.emu_dist_error.restype = C.c_char_p
+    import emu_build
+    L = C.CDLL(emu_build.build())
+    L.emu_last_error.restype = C.c_char_p
     L.emu_dist_matvec.restype = C.c_int
     L.emu_dist_matvec.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                   C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
@@ -77,7 +70,7 @@ def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = val
-    assert rc == 0, L.emu_dist_error().decode()
+    assert rc == 0, L.emu_last_error().decode()
     info = info.reshape(R, 8)
     assert int(info[:, 0].sum()) == n, "every node has exactly one owner"
     assert int(info[:, 2].sum()) == len(t.mv_lev), "every visited element belongs to exactly one rank"

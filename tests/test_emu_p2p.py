@@ -20,13 +20,8 @@ LIB = os.path.join(EMU, "_build", "libdkt_emu_p2p.so")
 
 
 def _lib():
-    srcs = [os.path.join(EMU, "emu_p2p.cpp"), os.path.join(EMU, "cuda_emu.cpp")]
-    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_p2p.cuh")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-shared",
-                               "-fPIC"] + srcs + ["-o", LIB])
-    L = C.CDLL(LIB)
+    import emu_build
+    L = C.CDLL(emu_build.build())
     L.emu_p2p_error.restype = C.c_char_p
     return L
 
