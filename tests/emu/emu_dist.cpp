@@ -25,7 +25,7 @@ struct Rank
 // nHangInterior, phased, number of chunk sets.
 extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const uint32_t *xyz, const uint8_t *lev, uint64_t n,
                                const double *ip0, const double *ip1, int R, int op_kind, const double *kref, double alpha, int dirichlet,
-                               double scale, const double *u, double *v, uint64_t n_global, uint64_t *info, int p2p)
+                               double scale, const double *u, double *v, uint64_t n_global, uint64_t *info, int p2p, int ghosted)
 {
   std::vector<std::unique_ptr<Rank>> ranks;
   int rc = DKT_OK;
@@ -55,8 +55,10 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
     for (int r = 0; r < R && rc == DKT_OK; r++)
     {
       Rank &me = *ranks[r];
-      cudaMalloc(&din[r], std::max<uint64_t>(me.dist.nOwned, 1) * sizeof(double));
-      cudaMalloc(&dout[r], std::max<uint64_t>(me.dist.nOwned, 1) * sizeof(double));
+      // ghosted: the caller's vectors hold [owned | ghosts] and are used in place (DKT_VEC_GHOSTED, what bench.py does)
+      const uint64_t len = me.dist.nOwned + (ghosted ? me.dist.nGhost : 0);
+      cudaMalloc(&din[r], std::max<uint64_t>(len, 1) * sizeof(double));
+      cudaMalloc(&dout[r], std::max<uint64_t>(len, 1) * sizeof(double));
       uint64_t *o = info + 8 * r;
       o[0] = me.dist.nOwned; o[1] = me.dist.nGhost; o[2] = me.da.nMv; o[3] = me.da.nHang; o[4] = me.da.nRegInterior; o[5] = me.da.nHangInterior;
       o[6] = me.da.phased ? 1 : 0; o[7] = me.da.sets.size();
@@ -67,7 +69,7 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
         for (uint64_t j = 0; j < ranks[r]->dist.nOwned; j++) din[r][j] = (epoch == 0 ? 0.5 : 1.0) * u[ranks[r]->dist.d_owned_gid[j]];
       for (unsigned stage = 1; stage <= 4 && rc == DKT_OK; stage <<= 1)
         for (int r = 0; r < R && rc == DKT_OK; r++)
-          rc = run_matvec_dist_stages(ranks[r]->da, ranks[r]->dist, &op, din[r], dout[r], scale, DKT_VEC_DEVICE, stage);
+          rc = run_matvec_dist_stages(ranks[r]->da, ranks[r]->dist, &op, din[r], dout[r], scale, DKT_VEC_DEVICE | (ghosted ? DKT_VEC_GHOSTED : 0u), stage);
     }
     if (rc == DKT_OK)
     {

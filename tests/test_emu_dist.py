@@ -27,7 +27,7 @@ def _lib():
     L.emu_last_error.restype = C.c_char_p
     L.emu_dist_matvec.restype = C.c_int
     L.emu_dist_matvec.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                  C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+                                  C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
     return L
 
 
@@ -63,7 +63,7 @@ def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
     try:
         L = _lib()
         rc = L.emu_dist_matvec(dim, order, md, 1 if case["sfc"] == "hilbert" else 0, p(xyz), p(lev), len(lev), p(ip0), p(ip1), R, 1, p(Kc),
-                               alpha, 1, 0.7, p(u), p(v), n, p(info), p2p)
+                               alpha, 1, 0.7, p(u), p(v), n, p(info), p2p, 1 if (p2p and R % 2) else 0)
     finally:
         for k, val in old.items():
             if val is None:
