@@ -4,6 +4,14 @@
 // Same recurrences and the same stopping rule (max-norm of the residual relative to max-norm of b).
 #include "dkt_internal.h"
 
+// also compiles under -DDKT_EMU (tests/emu/cuda_emu.h) for the CPU test-suite; never part of libdkt.so that way
+#ifdef DKT_EMU
+#include "cuda_emu.h"
+#define DKT_SOLVE_LAUNCH(kern, grid, stream) ::emu::make_launch(kern, (grid), 256, 0)
+#else
+#define DKT_SOLVE_LAUNCH(kern, grid, stream) kern<<<(grid), 256, 0, (stream)>>>
+#endif
+
 #include <cmath>
 #include <cstring>
 
@@ -141,10 +149,10 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
   *iters = 0;
   // normb, r0 = b - A x, p = r0
   CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
-  if (n) k_reduce3<<<grid, 256, 0, s>>>(nullptr, nullptr, nullptr, nullptr, d_b, n, red);
+  if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(nullptr, nullptr, nullptr, nullptr, d_b, n, red);
   rc = mv(d_x, Ap);
   if (rc) goto done;
-  if (n) k_cg_init<<<gridN, 256, 0, s>>>(d_b, Ap, n, r0, p);
+  if (n) DKT_SOLVE_LAUNCH(k_cg_init, gridN, s)(d_b, Ap, n, r0, p);
   g_launches += 2;
   reduce(rc);
   if (rc) goto done;
@@ -152,7 +160,7 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
     double normb = h[2];
     if (normb == 0.0) normb = 1.0;
     CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
-    if (n) k_reduce3<<<grid, 256, 0, s>>>(r0, r0, nullptr, nullptr, r0, n, red);  // red[0] = r0.r0, red[2] = |r0|
+    if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(r0, r0, nullptr, nullptr, r0, n, red);  // red[0] = r0.r0, red[2] = |r0|
     g_launches++;
     reduce(rc);
     if (rc) goto done;
@@ -163,13 +171,13 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
       rc = mv(p, Ap);
       if (rc) goto done;
       CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
-      if (n) k_reduce3<<<grid, 256, 0, s>>>(nullptr, nullptr, p, Ap, nullptr, n, red);  // red[1] = p.Ap
+      if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(nullptr, nullptr, p, Ap, nullptr, n, red);  // red[1] = p.Ap
       g_launches++;
       reduce(rc);
       if (rc) goto done;
       const double alpha = rr / h[1];
       CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
-      if (n) k_cg_step1<<<grid, 256, 0, s>>>(alpha, p, Ap, r0, n, d_x, r1, red);
+      if (n) DKT_SOLVE_LAUNCH(k_cg_step1, grid, s)(alpha, p, Ap, r0, n, d_x, r1, red);
       g_launches++;
       reduce(rc);
       if (rc) goto done;
@@ -178,7 +186,7 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
       if (resid <= *tol) { *status = 0; break; }
       const double beta = h[0] / rr;
       rr = h[0];
-      if (n) k_cg_step2<<<gridN, 256, 0, s>>>(beta, r1, n, p, r0);
+      if (n) DKT_SOLVE_LAUNCH(k_cg_step2, gridN, s)(beta, r1, n, p, r0);
       g_launches++;
     }
     *tol = resid;

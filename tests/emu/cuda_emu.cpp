@@ -21,19 +21,26 @@ State &state()
   return s;
 }
 
-void yield()
+static void leave(int why)
 {
   State &s = state();
   if (s.current < 0)
   {
-    fprintf(stderr, "emu: __syncthreads() in a kernel launched without fibers\n");
+    fprintf(stderr, "emu: __syncthreads() or a warp shuffle in a kernel launched without fibers\n");
     abort();
   }
-  s.barriers++;
   Fiber &f = s.fibers[s.current];
-  f.barriers++;
+  f.wait = why;
   swapcontext(&f.ctx, &s.sched);
 }
+void yield()
+{
+  State &s = state();
+  s.barriers++;
+  if (s.current >= 0) s.fibers[s.current].barriers++;
+  leave(1);
+}
+void spin_yield() { leave(2); }
 
 static void trampoline()
 {
@@ -43,16 +50,22 @@ static void trampoline()
   swapcontext(&s.fibers[s.current].ctx, &s.sched);
 }
 
+// Fibers run until they reach a barrier, spin or finish.  Fibers at a barrier stay there until every live fiber of the
+// block is at a barrier; spinning fibers get another turn every sweep.
 void run_block(unsigned nthreads, const std::function<void()> &body)
 {
   State &s = state();
   if (s.fibers.size() < nthreads) s.fibers.resize(nthreads);
   s.body = body;
+  s.nthreads = nthreads;
+  s.warps.assign((nthreads + 31) / 32, State::WarpX());
+  for (auto &w : s.warps) memset(&w, 0, sizeof(w));
   for (unsigned t = 0; t < nthreads; t++)
   {
     Fiber &f = s.fibers[t];
     if (!f.stack) f.stack = (char *)malloc(STACK);
     f.done = false;
+    f.wait = 0;
     f.barriers = 0;
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack;
@@ -62,19 +75,38 @@ void run_block(unsigned nthreads, const std::function<void()> &body)
   }
   std::vector<unsigned> order(nthreads);
   unsigned live = nthreads;
+  unsigned long idle_sweeps = 0;
   while (live)
   {
     std::iota(order.begin(), order.end(), 0u);
     if (s.order == 1) std::reverse(order.begin(), order.end());
     else if (s.order == 2) std::shuffle(order.begin(), order.end(), s.rng);
+    bool progress = false;
     for (unsigned t : order)
     {
       Fiber &f = s.fibers[t];
-      if (f.done) continue;
+      if (f.done || f.wait == 1) continue;
+      const int before = f.wait;
       s.current = (int)t;
       threadIdx.x = t;
       swapcontext(&s.sched, &f.ctx);
       if (f.done) live--;
+      if (f.done || f.wait != 2 || before != 2) progress = true;
+    }
+    // release the barrier once every live fiber has arrived
+    unsigned at = 0;
+    for (unsigned t = 0; t < nthreads; t++) at += (!s.fibers[t].done && s.fibers[t].wait == 1);
+    if (live && at == live)
+    {
+      for (unsigned t = 0; t < nthreads; t++) s.fibers[t].wait = 0;
+      progress = true;
+    }
+    idle_sweeps = progress ? 0 : idle_sweeps + 1;
+    if (idle_sweeps > 100000)
+    {
+      fprintf(stderr, "emu: block %u makes no progress (a warp shuffle whose partner never arrives, or threads stuck at different barriers)\n",
+              blockIdx.x);
+      abort();
     }
   }
   s.current = -1;

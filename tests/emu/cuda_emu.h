@@ -51,6 +51,7 @@ struct Fiber
   ucontext_t ctx;
   char *stack = nullptr;
   bool done = false;
+  int wait = 0;                // 0 runnable, 1 at a __syncthreads(), 2 spinning (warp shuffle rendezvous)
   unsigned long barriers = 0;  // __syncthreads() executed by this thread in the current block
 };
 struct State
@@ -64,9 +65,14 @@ struct State
   int order = 0;
   std::mt19937 rng{12345};
   uint64_t barriers = 0;
+  // warp shuffles: per lane the value, the number of shuffles posted and the number read (reset per block)
+  struct WarpX { uint64_t val[32]; unsigned posted[32], read[32]; };
+  std::vector<WarpX> warps;
+  unsigned nthreads = 0;
 };
 State &state();
 void yield();
+void spin_yield();  // give the other fibers a turn while waiting for one of them (not a barrier)
 void run_block(unsigned nthreads, const std::function<void()> &body);
 
 template <typename F>
@@ -142,6 +148,26 @@ template <typename T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = 
 template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
+inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+// warp shuffle between the fibers of one warp: post, wait for the partner's post, read, wait until the partner has read
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o)
+{
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  emu::State &s = emu::state();
+  const unsigned tid = threadIdx.x, lane = tid & 31u, partner = lane ^ (unsigned)o;
+  if ((tid & ~31u) + partner >= s.nthreads) return v;
+  emu::State::WarpX &x = s.warps[tid >> 5];
+  const unsigned gen = x.posted[lane] + 1;
+  x.val[lane] = 0;
+  memcpy(&x.val[lane], &v, sizeof(T));
+  x.posted[lane] = gen;
+  while (x.posted[partner] < gen) emu::spin_yield();
+  T r;
+  memcpy(&r, &x.val[partner], sizeof(T));
+  x.read[lane] = gen;
+  while (x.read[partner] < gen) emu::spin_yield();
+  return r;
+}
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) {}
 inline long long clock64() { static long long c = 0; return c += 1000; }

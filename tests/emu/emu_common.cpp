@@ -9,7 +9,6 @@ namespace dkt
 std::string g_emu_err;
 uint64_t g_launches = 0;
 void set_error(const std::string &msg) { g_emu_err = msg; }
-int cg_solve(DA &, Dist *, const dkt_op *, double *, const double *, int, double *, double, unsigned, int *, int *) { return DKT_ERR_UNSUPPORTED; }
 }  // namespace dkt
 extern "C" const char *emu_last_error() { return dkt::g_emu_err.c_str(); }
 extern "C" void emu_set_order(int order) { emu::state().order = order; }

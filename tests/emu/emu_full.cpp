@@ -72,6 +72,24 @@ extern "C" int emu_da_matvec(void *h, int kind, const double *kref, double alpha
   cudaFree(dout);
   return rc;
 }
+// dkt_cg_solve on device vectors (HeatMat::cgSolve, FEM/examples/src/heatMat.cpp:165-325)
+extern "C" int emu_da_cg(void *h, int kind, const double *kref, double alpha, int dirichlet, double *x, const double *b, int max_iter,
+                         double *tol, double scale, unsigned flags, int *iters, int *status)
+{
+  DA &d = *(DA *)h;
+  dkt_op op;
+  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  double *dx = nullptr, *db = nullptr;
+  cudaMalloc(&dx, d.nNodes * sizeof(double));
+  cudaMalloc(&db, d.nNodes * sizeof(double));
+  memcpy(dx, x, d.nNodes * sizeof(double));
+  memcpy(db, b, d.nNodes * sizeof(double));
+  const int rc = cg_solve(d, nullptr, &op, dx, db, max_iter, tol, scale, flags, iters, status);
+  memcpy(x, dx, d.nNodes * sizeof(double));
+  cudaFree(dx);
+  cudaFree(db);
+  return rc;
+}
 extern "C" void emu_da_destroy(void *h)
 {
   DA *da = (DA *)h;

@@ -27,6 +27,9 @@ def lib():
     L.emu_da_matvec.restype = C.c_int
     L.emu_da_matvec.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
     L.emu_da_destroy.argtypes = [C.c_void_p]
+    L.emu_da_cg.restype = C.c_int
+    L.emu_da_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double,
+                            C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -85,6 +88,17 @@ class EmuDA:
         if rc:
             raise RuntimeError("emu_da_matvec rc=%d: %s" % (rc, lib().emu_last_error().decode()))
         return out
+
+    def cg_solve(self, b, kref, alpha, max_iter, tol, x0=None, dirichlet=True, scale=1.0, flags=0):
+        """dkt_cg_solve: returns (x, iterations, residual, status)"""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros_like(b) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        kr = np.ascontiguousarray(np.asarray(kref, dtype=np.float64).ravel())
+        t, it, st = C.c_double(tol), C.c_int(0), C.c_int(0)
+        rc = lib().emu_da_cg(self._h, 1, _p(kr), alpha, int(dirichlet), _p(x), _p(b), max_iter, C.byref(t), scale, flags, C.byref(it), C.byref(st))
+        if rc:
+            raise RuntimeError("emu_da_cg rc=%d: %s" % (rc, lib().emu_last_error().decode()))
+        return x, it.value, t.value, st.value
 
     def close(self):
         if self._h:

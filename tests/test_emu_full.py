@@ -98,3 +98,32 @@ def test_emulated_pipeline_refuses_class_u():
         pytest.skip("generator did not produce a class-U tree")
     with pytest.raises(RuntimeError, match="class-U"):
         emu_full.EmuDA(xyz, lev, dim, 1, md)
+
+
+def test_emulated_cg_solver():
+    """dkt_cg_solve (HeatMat::cgSolve with resident vectors) under the emulation - the block reductions with warp shuffles
+    included: converges to the manufactured solution on a uniform grid and follows the oracle's iterates on an adaptive tree"""
+    import dkt
+    from test_gpu_parity import _oracle_cg
+    dim, md = 3, 10
+    xyz, lev = dkt.trees.uniform_tree(dim, 3, md)
+    da = emu_full.EmuDA(xyz, lev, dim, 1, md)
+    K = flat.laplace_kref(dim, 1)
+    t = flat.build_tables(xyz, lev, dim, 1, md)
+    xt = cases.input_vector(da.n_nodes)
+    xt[t.bdy_ids] = 0.0
+    b = da.matvec(xt, kref=K, alpha=dim - 2.0, dirichlet=True)
+    x, it, resid, status = da.cg_solve(b, K, dim - 2.0, max_iter=300, tol=1e-11)
+    assert status == 0 and resid <= 1e-11 and it < 300
+    assert np.abs(x - xt).max() <= 1e-8 * np.abs(xt).max()
+    da.close()
+    case = load_case("ex3-d3-p1-morton-3")
+    t = cases.oracle_tables_for(case)
+    da = emu_full.EmuDA(case["xyz"], case["lev"], 3, 1, case["max_depth"])
+    bb = cases.input_vector(da.n_nodes, seed=4)
+    bb[t.bdy_ids] = 0.0
+    xo, ito, ro = _oracle_cg(t, K, 1.0, bb, 12, 0.0)
+    xg, itg, rg, _ = da.cg_solve(bb, K, 1.0, max_iter=12, tol=0.0)
+    assert itg == ito == 12
+    assert np.abs(xg - xo).max() <= 1e-9 * np.abs(xo).max() and abs(rg - ro) <= 1e-9 * ro
+    da.close()
