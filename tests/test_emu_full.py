@@ -127,3 +127,50 @@ def test_emulated_cg_solver():
     assert itg == ito == 12
     assert np.abs(xg - xo).max() <= 1e-9 * np.abs(xo).max() and abs(rg - ro) <= 1e-9 * ro
     da.close()
+
+
+@pytest.mark.parametrize("seed", [46, 47, 49, 52, 55, 59])
+def test_emulated_pipeline_random_trees(seed):
+    """random 2:1-balanced trees (dims 2-4, orders 1-2, Morton / Hilbert, depths 8-14, phantom elements, a class-U one): the
+    emulated construction must equal the oracle's tables bit for bit, the matvec its vector"""
+    import dkt
+    tabs = {d: cases.sfc_tables_for(load_case(n)) for d, n in ((2, "ex1-d2-p1-hilbert-5"), (3, "ex3-d3-p1-hilbert-3"), (4, "ex3-d4-p1-hilbert-3"))}
+    rng = np.random.default_rng(9000 + seed)
+    dim = int(rng.choice([2, 3, 4]))
+    order = int(rng.choice([1, 2]))
+    hil = int(rng.integers(0, 2))
+    md = int(rng.choice([8, 10, 14]))
+    maxl = {2: 7, 3: 5, 4: 4}[dim] - (order == 2)
+    pts = rng.uniform(0, 1, (int(rng.integers(1, 4)), dim))
+    if rng.random() < 0.5:
+        pts[0] = rng.choice([0.0, 1.0], dim)
+    rad = rng.uniform(0, 0.35, len(pts))
+
+    def g(ctr):
+        d = np.full(len(ctr), 1e9)
+        for q, r in zip(pts, rad):
+            d = np.minimum(d, np.abs(np.sqrt(((ctr - q) ** 2).sum(axis=1)) - r))
+        return d
+
+    xyz, lev = dkt.trees._refine(np, dim, md, int(rng.integers(0, 3)), maxl, g)
+    perm = rng.permutation(len(lev))
+    xyz, lev = xyz[perm], lev[perm]
+    t = flat.build_tables(xyz, lev, dim, order, md, tabs[dim] if hil else None)
+    if t.tree_class == "U":
+        with pytest.raises(RuntimeError, match="class-U"):
+            emu_full.EmuDA(xyz, lev, dim, order, md, sfc=hil)
+        return
+    da = emu_full.EmuDA(xyz, lev, dim, order, md, sfc=hil)
+    e = da.export()
+    assert da.tree_class == t.tree_class and da.n_mv_elem == len(t.mv_lev) and da.n_hanging == len(t.hang_idx)
+    assert np.array_equal(e["elem_xyz"], t.elem_xyz) and np.array_equal(e["elem_lev"], t.elem_lev)
+    assert np.array_equal(e["node_xyz"], t.node_xyz) and np.array_equal(e["node_lev"], t.node_lev) and np.array_equal(e["bdy"], t.bdy_ids)
+    oe2n = np.where(t.e2n < 0, INVALID, t.e2n).astype(np.uint32)
+    for x, y in zip(_sorted_rows(e["mv_xyz"], e["mv_lev"], e["e2n"]), _sorted_rows(t.mv_xyz, t.mv_lev, oe2n)):
+        assert np.array_equal(x, y)
+    n = da.n_nodes
+    u = rng.uniform(-1, 1, n)
+    N = (order + 1) ** dim
+    K = rng.uniform(-1, 1, (N, N))
+    assert rel(da.matvec(u, kref=K, alpha=1.3, scale=0.6, dirichlet=True), flat.matvec(t, u, K, alpha=1.3, scale=0.6, dirichlet=True)) <= TOL
+    da.close()
