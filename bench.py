@@ -152,75 +152,13 @@ def weak_window(n_gpus, per_gpu_elems):
     return min(max(w, 1.0 / 512), 0.5)
 
 
-def groups_probe(args):
-    """Internal mode (bench.py --groups-probe G): ONE GPU, the bench tree, the opt-in sibling-group tables
-    (DKT_GROUPS=G, dkt_chunks.cu) timed beside the default per-element tables on the same input, and the two
-    output vectors compared.  Runs in its own process so that the main measurement cannot be affected."""
-    import torch
-    import dkt
-    from dkt import operators
-    torch.cuda.set_device(0)
-    level = args.level
-    width = weak_window(1, args.per_gpu_elems) if level == 9 else 0.5
-    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH, use_torch=True, t0=0.5 - width / 2, t1=0.5 + width / 2)
-    torch.cuda.synchronize()
-    op = dkt.Operator.dense(operators.laplace_kref(DIM, ORDER), alpha=DIM - 2.0)
-    out = {"groups": args.groups_probe, "level": level}
-    res = {}
-    for name, g in (("default", 0), ("groups", args.groups_probe)):
-        os.environ["DKT_GROUPS"] = str(g)
-        da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH)
-        n = da.n_nodes
-        stream = torch.cuda.Stream()
-        torch.cuda.set_stream(stream)
-        da.set_stream(stream.cuda_stream)
-        u = torch.rand(n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(99)) * 2 - 1
-        v = torch.zeros_like(u)
-        for _ in range(args.warmup):
-            da.matvec(op, u, v)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            da.matvec(op, u, v)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        res[name] = v.clone()
-        out[name] = {"ms_per_step": ms, "dof_per_s": n / (ms * 1e-3), "alg_gbs": da.alg_bytes / (ms * 1e-3) / 1e9,
-                     "chunks": da.chunk_info()}
-        da.close()
-    d = (res["groups"] - res["default"]).abs().max().item() / res["default"].abs().max().item()
-    out["max_rel_diff_vs_default"] = d
-    print(json.dumps(out))
-
-
-def run_groups_probe_subprocess(args, g="2", timeout=180):
-    """The experimental leg of the default run: never raises, never touches the headline numbers."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--groups-probe", str(g), "--steps", str(min(args.steps, 10)), "--warmup", "3",
-           "--level", str(args.level), "--per-gpu-elems", str(args.per_gpu_elems)]
-    env = dict(os.environ)
-    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
-        env.pop(k, None)
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
-        for ln in reversed(r.stdout.strip().splitlines()):
-            if ln.startswith("{"):
-                return json.loads(ln)
-        return {"groups": g, "error": ("rc=%d " % r.returncode) + (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
-    except subprocess.TimeoutExpired:
-        return {"groups": g, "error": "timeout after %d s" % int(timeout)}
-    except Exception as e:
-        return {"groups": g, "error": repr(e)[:300]}
-
-
 def run_gpu(args):
     import numpy as np
     import torch
     import dkt
     from dkt import operators
-    if args.groups != "0":
-        os.environ["DKT_GROUPS"] = str(args.groups)
+    if args.families is not None:
+        os.environ["DKT_FAMILIES"] = str(args.families)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -351,15 +289,15 @@ def run_gpu(args):
                        "n_hanging_elem": int(n_hang_total), "n_ghost_nodes": int(n_ghost_total), "tree_class": da.tree_class,
                        "partition": "SFC-contiguous element ranges, one per GPU; NCCL send/recv ghost exchange" if world > 1 else "single GPU",
                        "cache": "working set %.0f MB per GPU > 126 MB L2 (no flush needed)" % (alg_total / world / 1e6),
-                       "groups": args.groups,
+                       "tables": "per-element (DKT_FAMILIES=0)" if os.environ.get("DKT_FAMILIES") == "0" else "sibling families + singles",
                        "tree_build_s": round(t_tree, 3), "da_build_s": round(t_build, 3), "chunks_rank0": da.chunk_info()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # ncu dram__bytes_read+write of the step's kernels on the default workload (profiles/README.md);
                          # None for other workloads
-                         "traffic": 1.78e9 if (world == 1 and level == 9 and args.per_gpu_elems == 1.2e7 and args.groups == "0") else None,
+                         "traffic": None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                          "alg_bytes_per_step_per_gpu": alg_total / world,
-                         "kernel": "whole matvec step per GPU (memset + chunked regular + hanging kernels" +
+                         "kernel": "whole matvec step per GPU (memset + family kernel + per-element kernels of the singles" +
                                    (" + ghost pack/NCCL/unpack)" if world > 1 else ")")},
             "e2e": {"value": n_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global,
                     "ms_per_step": e2e_s * 1e3, "max_rel_diff_vs_device_path": check},
@@ -374,16 +312,6 @@ def run_gpu(args):
                 line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
             except Exception as e:  # the bench line must survive a missing oracle
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
-        if args.experimental and world == 1 and args.groups == "0":
-            # opt-in sibling-group tables (DKT_GROUPS, validated against the oracle in the CPU emulation, tests/test_emu_chunks.py):
-            # timed in a separate process AFTER the headline measurement; informational only
-            deadline = time.time() + 120.0  # the whole experimental leg is bounded; what does not fit is skipped
-            probes = []
-            for g in ("2", "2,1", "3,2"):
-                left = deadline - time.time()
-                probes.append(run_groups_probe_subprocess(args, g=g, timeout=min(90.0, left)) if left > 20.0
-                              else {"groups": g, "error": "skipped: time budget of the experimental leg used up"})
-            line["experimental_groups"] = probes
         print(json.dumps(line))
     da.close()
     if dist is not None:
@@ -400,14 +328,10 @@ def main():
     ap.add_argument("--per-gpu-elems", type=float, default=1.2e7, help="weak scaling: target elements per GPU (level 9)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: replicas (0 = one per core, at most 64)")
-    ap.add_argument("--groups", default="0", help="build the DA with sibling-group tables (DKT_GROUPS=g or gR,gH; opt-in)")
-    ap.add_argument("--groups-probe", default="", help=argparse.SUPPRESS)
-    ap.add_argument("--no-experimental", dest="experimental", action="store_false",
-                    help="skip the separate-process timing of the opt-in sibling-group tables")
+    ap.add_argument("--families", type=int, default=None, choices=[0, 1],
+                    help="0: per-element chunk tables only (DKT_FAMILIES=0); default: sibling-family tables")
     args = ap.parse_args()
-    if args.groups_probe:
-        groups_probe(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -327,14 +327,16 @@ extern "C"
     CKA(cudaEventElapsedTime(ms, da->d.ev0, da->d.ev1));
     return DKT_OK;
   }
-  int dkt_da_chunk_info(const dkt_da *da, uint64_t out[10])
+  int dkt_da_chunk_info(const dkt_da *da, uint64_t out[16])
   {
     if (!da || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
-    // aggregated over the regular sets (out[0..4]) and the hanging sets (out[5..9])
-    for (int i = 0; i < 10; i++) out[i] = 0;
+    // aggregated over the regular per-element sets (out[0..4]), the hanging ones (out[5..9]) and the sibling-family sets
+    // (out[10..14]; out[15] = elements in families)
+    for (int i = 0; i < 16; i++) out[i] = 0;
     for (const ChunkSet &cs : da->d.sets)
     {
-      uint64_t *o = out + (cs.rows == 1 ? 0 : 5);
+      uint64_t *o = out + (cs.kind == 2 ? 10 : cs.rows == 1 ? 0 : 5);
+      if (cs.kind == 2) out[15] += cs.nElem << da->d.dim;
       o[0] += cs.nChunks; o[1] = cs.elemsPerChunk; o[2] = std::max<uint64_t>(o[2], cs.maxNloc);
       o[3] = std::max<uint64_t>(o[3], cs.maxLen); o[4] += cs.totalNodes;
     }

@@ -1,23 +1,35 @@
-// The production matvec: SFC-contiguous element CHUNKS staged through shared memory by
-// persistent, software-pipelined CTAs.
+// The production matvec: SFC-contiguous CHUNKS of the tree staged through shared memory.
 //
 // Why: the flat kernels (dkt_matvec.cu) issue (order+1)^dim scattered 8-byte gathers and fp64
 // atomics per element straight to L1/L2 and are L1TEX/atomic bound at ~15 % of the HBM roofline
 // (profiles/r01_*).  Shared-memory fp64 atomics are CAS spin loops on sm_100a
 // (ATOMS.CAST.SPIN.64), so the in-chunk reduction is made atomic-free instead.
 //
-//   build (once per DA): every set of UNITS (elements, or sibling groups - see below) first gets a
-//   "unit slot table" U[unit][slot] = node id (k_unit_slots_*), then k_chunk_build (one CTA per chunk,
-//   cub::BlockRadixSort in shared memory) turns it into the chunk tables:
+// Two table layouts feed two kernel families:
+//
+// (1) SIBLING FAMILIES (order 1, the default wherever it applies; k_mvf).  A complete family - the 2^dim leaves of
+//     one parent - shares a 3^dim node lattice.  One UNIT is a family: 3^dim lattice slots (81 in 4-D) instead
+//     of 2^dim x 2^dim element slots (256), 16-bit table entries, and no separate parent-lattice slots for hanging
+//     elements: the parent's nodes ARE the corners of the family lattice, a hanging point is interpolated from them
+//     when the lattice is filled, and the transposed interpolation runs on the summed lattice in registers.  Quirk Q1
+//     of the reference (FEM/include/matvec.h:517) reduces, on such a family, to ONE scalar per child subtracted
+//     from its corner node (derivation at k_family_check, which admits only families where it holds).  Elements
+//     outside such families ("singles") keep layout (2).
+//
+// (2) PER-ELEMENT sets (every order; k_mv3): one unit is an element, regular and hanging elements in separate sets.
+//
+//   build (once per DA): every set of UNITS first gets a "unit slot table" U[unit][slot] = node id
+//   (k_unit_slots_elem, k_family_units), then k_chunk_build (one CTA per chunk, cub::BlockRadixSort in shared
+//   memory) turns it into the chunk tables:
 //     * the chunk's slots are sorted by the node they touch -> unique nodes, run length `len` of each node
 //     * nodes are re-ranked by (len descending, id ascending): jagged-diagonal storage.  The k-th
-//       contribution to node n lives at X[jd[k] + n]; jd[k] = number of (node, j<k) pairs.
-//     * every slot gets one 32-bit word  n | (jd[k] + n) << 16 ; words are stored slot-major
-//       inside the chunk so that a warp reads 32 consecutive words
-//     * every node gets its global id and a meta word: len | boundary bit | shared-with-another-
-//       chunk bit (global reference count != len)
+//       contribution to node n lives at position jd[k] + n; jd[k] = number of (node, j<k) pairs.
+//     * per-element sets: every slot gets one 32-bit word  n | (jd[k] + n) << 16, stored slot-major; every node
+//       its global id and a meta word: len | boundary bit | shared-with-another-chunk bit
+//     * family sets: rk16[slot] = n, inv16[jd[k] + n] = shared-memory address of the contributing lattice point,
+//       one 32-bit record gid | boundary | shared per node, [jd | cnt] with cnt[k] = #nodes with a run longer than k
 //
-//   matvec (k_mv3, persistent CTAs looping over chunks c = blockIdx.x, +gridDim.x, ...):
+//   per-element matvec (k_mv3, persistent CTAs looping over chunks c = blockIdx.x, +gridDim.x, ...):
 //     T0  wait for the cp.async gather of this chunk's node values, barrier
 //     T1  load the NEXT chunk's node ids / meta into registers (overlaps T2)
 //     T2  thread per element: ein[r] = un[n] (LDS), K_e, X[pos] = eout[r] (STS; every slot owns
@@ -27,10 +39,11 @@
 //     T4  barrier; thread per node: acc = sum_k X[jd[k] + n]  (lanes read consecutive words;
 //         neighbouring lanes have equal len, so no divergence) and ONE plain store (node private
 //         to the chunk) or ONE fp64 RED (shared) per (chunk, node)
+//   family matvec: see k_mvf.
 //
 // Global atomics drop from N per element to ~2-3 per element in 4-D (the chunk surface).
 //
-// Order-1 extras (all build-time table tricks, no extra kernel work):
+// Order-1 extras of the per-element sets (all build-time table tricks, no extra kernel work):
 //   * XOR slot schedule: slot s of an element with Morton child number c holds lattice rank s ^ c, so
 //     sibling elements read the SAME node in the same instruction (shared-memory broadcast).  The
 //     identity and Walsh-Hadamard operator forms commute with that permutation, and the parent->child
@@ -46,12 +59,6 @@
 // Partitioned DAs build three phases of sets (interior first half / boundary / interior second half)
 // so that dkt_dist.cu can run the ghost exchanges beside the interior elements.
 //
-// SIBLING GROUPS (order 1, opt-in: environment DKT_GROUPS=g at DA construction; see k_mvg below): the
-// 2^g leaves of a complete sibling family that agree in the child-number bits of the dimensions >= g are ONE
-// unit handled by one thread.  They share a 3^g x 2^(dim-g) node lattice, so a quad (dim 4, g = 2) needs 36
-// gathers and 36 scatters where four separate elements need 64 + 64, and a hanging group reads the 16 parent
-// nodes once.  Elements outside complete families stay in per-element sets.
-//
 // This file also compiles under -DDKT_EMU with tests/emu/cuda_emu.h (fibers on the CPU) - that build exists
 // ONLY so the CPU test-suite can execute the table construction and the kernels' logic against the oracle;
 // it is never part of libdkt.so.
@@ -63,7 +70,7 @@
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 #define DKT_LAUNCH(k, g, b, s, st) k<<<(g), (b), (s), (st)>>>
-#define DKT_DYN_SMEM(type, name) extern __shared__ type name[]
+#define DKT_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
 #include <algorithm>
@@ -85,34 +92,40 @@ namespace dkt
   } while (0)
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                       // per-element sets: 4096 slots per chunk
-constexpr int SORT_ITEMS_GRP = 20;                   // sibling-group sets: 5120 slots per chunk (128 quads of 36, 96 hanging quads of 52)
+constexpr int SORT_ITEMS = 16;                       // 4096 slots per chunk
 constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;
-constexpr int SLOT_CAP_GRP = SORT_THREADS * SORT_ITEMS_GRP;
 constexpr int MAX_LEN = 511;                         // run length of a node inside a chunk (9 bits)
 constexpr uint32_t META_LEN = 0x1FFu;
 constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty: only read by this chunk)
 constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
-constexpr uint32_t REC_SHARED = 0x80000000u, REC_BDY = 0x40000000u, REC_GID = 0x3FFFFFFFu;  // group sets: 4-byte node records
+constexpr uint32_t REC_SHARED = 0x80000000u, REC_BDY = 0x40000000u, REC_GID = 0x3FFFFFFFu;  // family sets: 4-byte node records
 constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
-#ifndef DKT_GRP_TPB
-#define DKT_GRP_TPB 128  // threads (= units per chunk at most) of the group kernels; 96 lets three CTAs of regular quads share an SM
-#endif
-constexpr int GRP_TPB = DKT_GRP_TPB;
-// units per chunk of a group set with `spu` slots per unit (groups of 2^g leaves): what the block sort holds, at most
-// 512 elements in 4-D / 1024 below (the chunk's nodes are double-buffered in shared memory: with more, two CTAs no longer
-// fit on an SM), rounded down to whole warps when that costs at most an eighth; threads of its kernel: the next multiple of 32
-constexpr int grp_upc(int spu, int dim, int g)
+
+// Sibling-family sets.  The 3^dim lattice of a family lives in shared memory at  Ls[f * S + p0 + 3 p1 + SA p2 + SB p3];
+// one thread (a "quad") handles the 4 children that differ in dimensions 0 and 1, the 2^(dim-2) quads of a family are
+// neighbouring lanes.  S, SA, SB make every 8-byte access of the quad phase conflict-free (searched, half-warp model:
+// tools/smem_sim.py validated that model against ncu in round 1).
+template <int DIM>
+struct Fam
 {
-  int u = SORT_THREADS * SORT_ITEMS_GRP / spu;
-  if (u > GRP_TPB) u = GRP_TPB;
-  const int cap = (dim >= 4 ? 512 : 1024) >> g;
-  if (u > cap) u = cap;
-  const int r = u & ~31;
-  return (r > 0 && (u - r) * 8 <= u) ? r : u;
-}
-constexpr int grp_tpb(int spu, int dim, int g) { return (grp_upc(spu, dim, g) + 31) & ~31; }
+  static constexpr int NL = DIM - 2;                 // dimensions spread over lanes
+  static constexpr int QPF = 1 << NL;                // quads (threads) per family
+  static constexpr int FPW = 32 / QPF;               // families per warp
+  static constexpr int L = (DIM == 2 ? 9 : DIM == 3 ? 27 : 81);
+  static constexpr int SA = (DIM == 4 ? 10 : 12), SB = 36;
+  static constexpr int S = (DIM == 2 ? 9 : DIM == 3 ? 33 : 101);
+  static constexpr int N = 1 << DIM;
+  static constexpr int NS = 1 << NL;                 // (s2, s3) combinations: lattice points of a quad = 9 * NS
+  static constexpr int TPB = 128;
+  static constexpr int UPC = TPB / QPF;              // families per chunk (32 / 64 / 128: 512 elements)
+};
+__host__ __device__ constexpr int fam_L(int dim) { return dim == 2 ? 9 : dim == 3 ? 27 : 81; }
+__host__ __device__ constexpr int fam_S(int dim) { return dim == 2 ? 9 : dim == 3 ? 33 : 101; }
+__host__ __device__ constexpr int fam_SA(int dim) { return dim == 4 ? 10 : 12; }
+__host__ __device__ constexpr int fam_UPC(int dim) { return 128 >> (dim - 2); }
+// natural lattice index k = p0 + 3 p1 + 9 p2 + 27 p3  ->  offset inside the family's shared-memory lattice
+__host__ __device__ constexpr int fam_laddr(int dim, int k) { return (k % 9) + fam_SA(dim) * ((k / 9) % 3) + 36 * (k / 27); }
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
@@ -125,17 +138,8 @@ constexpr int grp_tpb(int spu, int dim, int g) { return (grp_upc(spu, dim, g) + 
 #ifndef DKT_HANG_MINB
 #define DKT_HANG_MINB 4
 #endif
-// resident CTAs per SM the group kernels are compiled for.  ptxas, 4-D: 2 -> 220 (regular quads) / 255 (hanging quads) /
-// 220 (hanging pairs) registers, no spills; 3 -> 168 registers: regular quads and hanging pairs without spills, hanging
-// quads 0.6 KB of spills (profiles/r01_ptxas_groups.txt)
-#ifndef DKT_GRP_RSHARE
-#define DKT_GRP_RSHARE 1  // regular groups: shared butterflies along the XOR-permuted dimensions (see k_mvg)
-#endif
-#ifndef DKT_GRP_MINB_REG
-#define DKT_GRP_MINB_REG 2
-#endif
-#ifndef DKT_GRP_MINB_HANG
-#define DKT_GRP_MINB_HANG 2
+#ifndef DKT_FAM_MINB
+#define DKT_FAM_MINB 3   // resident CTAs per SM the family kernel is compiled for
 #endif
 int rows_per_chunk(int N)
 {
@@ -193,14 +197,15 @@ __global__ void k_unit_slots_elem(const uint32_t *e2n, const uint32_t *pnode, co
 }
 
 // One CTA per chunk of `upc` units with `spu` slots each (U is unit-major).  WRITE == false: only report the
-// chunk's node count and longest run.  split16: the slot words are stored as two 16-bit arrays (node rank /
-// position), two slots per 32-bit word, the node records as ONE 32-bit word gid | boundary bit | shared bit, and the jd table is
-// followed by cnt[k] = #nodes with a run longer than k, which replaces the run length of the records (group sets).
+// chunk's node count and longest run.  fam != 0 (family sets, fam = dim): the tables are rk16[slot] = node rank (unit-major,
+// i.e. in U's order) and inv16[position] = shared-memory address of the lattice point that contributes at that
+// jagged-diagonal position, the node records ONE 32-bit word gid | boundary bit | shared bit, and the jd table is followed by
+// cnt[k] = #nodes with a run longer than k, which replaces the run length of the records.
 template <bool WRITE, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16, const uint32_t *refcnt, const uint8_t *isbdy,
+k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, const uint32_t *refcnt, const uint8_t *isbdy,
               const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out, uint32_t *slot, uint16_t *rk16,
-              uint16_t *ps16, uint32_t *gid_out, uint16_t *meta_out, uint32_t *rec_out, uint16_t *jd_out)
+              uint16_t *inv16, uint32_t *gid_out, uint16_t *meta_out, uint32_t *rec_out, uint16_t *jd_out)
 {
   constexpr int CAP = SORT_THREADS * ITEMS;
   using SortPairs = cub::BlockRadixSort<uint32_t, SORT_THREADS, ITEMS, uint16_t>;
@@ -366,7 +371,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
     for (int k = 0; k <= ml; k++)
     {
       const int cnt = s_jd[k];
-      if (k < 16)
+      if (k < 16 && !fam)
         while ((acc & 15) != k) acc++;
       s_jd[k] = acc;
       acc += cnt;
@@ -375,9 +380,9 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
   }
   __syncthreads();
   const uint64_t noff = node_off[c];
-  if (!split16)
+  if (!fam)
     for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS) jd_out[c * (uint64_t)jdStride + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
-  else  // group sets: [jd | cnt] per chunk; the node records carry no run length, cnt[] gives it (nodes are ranked by it)
+  else  // family sets: [jd | cnt] per chunk; the node records carry no run length, cnt[] gives it (nodes are ranked by it)
     for (int k = threadIdx.x; k < jdStride; k += SORT_THREADS)
     {
       jd_out[c * (uint64_t)(2 * jdStride) + k] = (uint16_t)s_jd[min(k, MAX_LEN + 1)];
@@ -401,12 +406,12 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
       nr = s_newrank[n0];
       if (wr[i]) pos = (uint32_t)s_jd[k] + nr;
     }
-    if (!split16) slot[u0 * spu + (uint64_t)q * upc + el] = nr | (pos << 16);
+    if (!fam) slot[u0 * spu + (uint64_t)q * upc + el] = nr | (pos << 16);
     else
     {
-      const uint64_t w16 = (u0 * (uint64_t)(spu / 2) + (uint64_t)(q >> 1) * upc + el) * 2 + (q & 1);
-      rk16[w16] = (uint16_t)nr;
-      ps16[w16] = (uint16_t)pos;
+      const uint64_t cbase = c * (uint64_t)upc * spu;
+      rk16[cbase + sv] = (uint16_t)nr;
+      if (key[i] != INVALID) inv16[cbase + pos] = (uint16_t)(el * fam_S(fam) + fam_laddr(fam, q));  // every family slot writes
     }
     if (key[i] != INVALID && head[i])
     {
@@ -415,7 +420,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int split16,
       uint32_t m = (uint32_t)len | META_PRESENT;
       if (refcnt[key[i]] != (uint32_t)len) m |= META_SHARED;
       if (isbdy[key[i]]) m |= META_BDY;
-      if (!split16)
+      if (!fam)
       {
         gid_out[noff + nr] = key[i];
         meta_out[noff + nr] = (uint16_t)m;
@@ -441,13 +446,18 @@ __global__ void k_max_u32(const uint32_t *in, uint64_t n, uint32_t *out)
   atomicMax(out, v);
 #endif
 }
+__global__ void k_pad4_widen(const uint32_t *in, uint64_t n, uint64_t *out)
+{
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (in[i] + 3u) & ~3u;
+}
 
 // Chunk tables of one set from its unit slot table U (freed by the caller).
 static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *refcnt)
 {
   const uint64_t nSet = cs.nElem;
   if (nSet == 0) return DKT_OK;
-  const int spu = cs.spu, upc = (int)cs.elemsPerChunk, split16 = cs.kind == 1 ? 1 : 0;
+  const int spu = cs.spu, upc = (int)cs.elemsPerChunk, fam = cs.kind == 2 ? da.dim : 0;
   cs.nChunks = (uint32_t)((nSet + upc - 1) / upc);
   uint32_t *nloc = nullptr, *mlen = nullptr;
   uint64_t *wide = nullptr, *off = nullptr;
@@ -455,13 +465,15 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   CK(cudaMalloc((void **)&mlen, (size_t)cs.nChunks * sizeof(uint32_t)));
   CK(cudaMalloc((void **)&wide, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
   CK(cudaMalloc((void **)&off, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
-  auto kcount = split16 ? k_chunk_build<false, SORT_ITEMS_GRP> : k_chunk_build<false, SORT_ITEMS>;
-  auto kwrite = split16 ? k_chunk_build<true, SORT_ITEMS_GRP> : k_chunk_build<true, SORT_ITEMS>;
-  DKT_LAUNCH(kcount, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, split16, refcnt, da.d_node_isbdy, nullptr, 0, nloc, mlen,
+  auto kcount = k_chunk_build<false, SORT_ITEMS>;
+  auto kwrite = k_chunk_build<true, SORT_ITEMS>;
+  DKT_LAUNCH(kcount, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, nullptr, 0, nloc, mlen,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
   CK(cudaMemsetAsync(wide, 0, ((size_t)cs.nChunks + 1) * sizeof(uint64_t), da.stream));
-  DKT_LAUNCH(k_u32_widen, nblk(cs.nChunks), 256, 0, da.stream)(nloc, cs.nChunks, wide);
+  // family sets: every chunk's node records start at a multiple of 16 bytes (cp.async.bulk)
+  if (fam) DKT_LAUNCH(k_pad4_widen, nblk(cs.nChunks), 256, 0, da.stream)(nloc, cs.nChunks, wide);
+  else DKT_LAUNCH(k_u32_widen, nblk(cs.nChunks), 256, 0, da.stream)(nloc, cs.nChunks, wide);
   g_launches++;
   int rc = device_exclusive_scan(da, wide, off, (uint64_t)cs.nChunks + 1);
   if (rc) return rc;
@@ -482,7 +494,7 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   cs.totalNodes = total;
   cs.d_node_off = off;
   const size_t nslotsAll = (size_t)cs.nChunks * upc * spu;
-  if (!split16)
+  if (!fam)
   {
     CK(cudaMalloc((void **)&cs.d_slot, nslotsAll * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&cs.d_gid, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
@@ -491,17 +503,22 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   else
   {
     CK(cudaMalloc((void **)&cs.d_rk16, nslotsAll * sizeof(uint16_t)));
-    CK(cudaMalloc((void **)&cs.d_ps16, nslotsAll * sizeof(uint16_t)));
-    CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 1) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&cs.d_inv16, nslotsAll * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 4) * sizeof(uint32_t)));
+    // bytes the kernel's bulk copies read but the build does not write (tail of the last chunk, padding records)
+    CK(cudaMemsetAsync(cs.d_rk16, 0, nslotsAll * sizeof(uint16_t), da.stream));
+    CK(cudaMemsetAsync(cs.d_inv16, 0, nslotsAll * sizeof(uint16_t), da.stream));
+    CK(cudaMemsetAsync(cs.d_rec, 0, std::max<uint64_t>(total, 4) * sizeof(uint32_t), da.stream));
+    cs.d_nloc = nloc;
   }
-  CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * (split16 ? 2 : 1) * sizeof(uint16_t)));
-  DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, split16, refcnt, da.d_node_isbdy, off, (int)cs.jdStride, nullptr,
-                                                              nullptr, cs.d_slot, cs.d_rk16, cs.d_ps16, cs.d_gid, cs.d_meta, (uint32_t *)cs.d_rec,
+  CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * (fam ? 2 : 1) * sizeof(uint16_t)));
+  DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, off, (int)cs.jdStride, nullptr,
+                                                              nullptr, cs.d_slot, cs.d_rk16, cs.d_inv16, cs.d_gid, cs.d_meta, (uint32_t *)cs.d_rec,
                                                               cs.d_jd);
   g_launches++;
   CK(cudaStreamSynchronize(da.stream));
   CK(cudaGetLastError());
-  cudaFree(nloc);
+  if (!fam) cudaFree(nloc);
   cudaFree(mlen);
   cudaFree(wide);
   cudaFree(dmax);
@@ -514,13 +531,17 @@ void free_chunks(DA &da)
   cudaFree(da.d_fmask);
   da.d_mv_child = nullptr;
   da.d_fmask = nullptr;
-  for (ChunkSet &cs : da.sets)
+  for (std::vector<ChunkSet> *sets : {&da.sets, &da.sets_elem})
   {
-    cudaFree(cs.d_slot); cudaFree(cs.d_gid); cudaFree(cs.d_meta); cudaFree(cs.d_jd); cudaFree(cs.d_node_off);
-    cudaFree(cs.d_rk16); cudaFree(cs.d_ps16); cudaFree(cs.d_rec);
-    for (void *p : cs.owned) cudaFree(p);
+    for (ChunkSet &cs : *sets)
+    {
+      cudaFree(cs.d_slot); cudaFree(cs.d_gid); cudaFree(cs.d_meta); cudaFree(cs.d_jd); cudaFree(cs.d_node_off);
+      cudaFree(cs.d_rk16); cudaFree(cs.d_inv16); cudaFree(cs.d_frec); cudaFree(cs.d_nloc); cudaFree(cs.d_rec);
+      for (void *p : cs.owned) cudaFree(p);
+    }
+    sets->clear();
   }
-  da.sets.clear();
+  da.families = false;
   if (da.ev_fork) cudaEventDestroy(da.ev_fork);
   da.ev_fork = nullptr;
   for (int a = 0; a < DA::MAX_AUX; a++)
@@ -541,8 +562,7 @@ __global__ void k_child_numbers(const uint32_t *xyz, const uint8_t *lev, uint64_
   for (int d = 0; d < dim; d++) c |= ((xyz[i * dim + d] >> (max_depth - L)) & 1u) << d;
   child[i] = (uint8_t)(L ? c : 0);
 }
-
-// ---- sibling groups: discovery ---------------------------------------------------------------
+// ---- sibling families: discovery -------------------------------------------------------------
 // d_mv_src is the position of every visited element in the visit (SFC) order (minus mv_src0 on a partitioned
 // DA); a complete family of leaves is 2^dim consecutive positions with one parent.
 __global__ void k_invert_src(const uint32_t *src, uint64_t n, uint64_t base, uint32_t *inv)
@@ -585,9 +605,9 @@ __global__ void k_family_heads(const uint32_t *inv, const uint32_t *xyz, const u
   }
   head[j] = h;
 }
-// mem[f * 2^dim + c] = visited-element index of child c of family f; infam[e] = 1
+// mem[f * 2^dim + c] = visited-element index of child c of family f
 __global__ void k_family_members(const uint32_t *inv, const uint64_t *head, const uint64_t *fpos, const uint8_t *child, uint64_t n, int dim,
-                                 uint32_t *mem, uint8_t *infam)
+                                 uint32_t *mem)
 {
   uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (j >= n || !head[j]) return;
@@ -597,7 +617,6 @@ __global__ void k_family_members(const uint32_t *inv, const uint64_t *head, cons
   {
     const uint32_t b = inv[j + t];
     mem[f * nch + child[b]] = b;
-    infam[b] = 1;
   }
 }
 // class of a unit: bit 1 = hanging, bit 0 = boundary (touches a ghost node; partitioned DA with comm/compute overlap).
@@ -607,28 +626,6 @@ __device__ __forceinline__ int elem_class(uint64_t e, uint64_t nReg, uint64_t nR
   const int hang = e >= nReg;
   const int bdy = phased && (hang ? (e - nReg >= nHangInt) : (e >= nRegInt));
   return (hang << 1) | bdy;
-}
-// mode 0: plain.  mode 1 (groups of 2^g with smaller hanging groups to follow): hanging groups get class 255.
-// mode 2 (the smaller groups, gOuter > g): groups inside a REGULAR outer group get class 255 - that one has them.
-__global__ void k_group_class(const uint32_t *mem, uint64_t nGroups, int dim, int g, int gOuter, int mode, uint64_t nReg, uint64_t nRegInt,
-                              uint64_t nHangInt, int phased, uint8_t *cls)
-{
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= nGroups) return;
-  const int NR = 1 << (dim - g), NC = 1 << g;
-  const uint64_t f = u / NR;
-  const int cR = (int)(u % NR);
-  int c = 0;
-  for (int cG = 0; cG < NC; cG++) c |= elem_class(mem[(f << dim) + ((cR << g) | cG)], nReg, nRegInt, nHangInt, phased);
-  if (mode == 1 && (c & 2)) c = 255;
-  if (mode == 2)
-  {
-    const int cRo = cR >> (gOuter - g);
-    bool outerHang = false;
-    for (int cG = 0; cG < (1 << gOuter); cG++) outerHang |= mem[(f << dim) + ((cRo << gOuter) | cG)] >= nReg;
-    if (!outerHang) c = 255;
-  }
-  cls[u] = (uint8_t)c;
 }
 // the elements outside complete families: class as above, 255 for family members
 __global__ void k_single_class(const uint8_t *infam, uint64_t n, uint64_t nReg, uint64_t nRegInt, uint64_t nHangInt, int phased,
@@ -643,18 +640,6 @@ __global__ void k_class_flags(const uint8_t *cls, uint64_t n, int want, uint64_t
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i > n) return;
   flag[i] = (i < n && cls[i] == want) ? 1 : 0;
-}
-// member lists of the selected groups, in (family, cR) order
-__global__ void k_group_list(const uint32_t *mem, const uint64_t *flag, const uint64_t *pos, uint64_t nGroups, int dim, int g,
-                             uint32_t *list)
-{
-  uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (u >= nGroups || !flag[u]) return;
-  const int NR = 1 << (dim - g), NC = 1 << g;
-  const uint64_t f = u / NR;
-  const int cR = (int)(u % NR);
-  uint32_t *dst = list + pos[u] * NC;
-  for (int cG = 0; cG < NC; cG++) dst[cG] = mem[(f << dim) + ((cR << g) | cG)];
 }
 __global__ void k_compact(const uint64_t *flag, const uint64_t *pos, uint64_t n, uint32_t *list)
 {
@@ -675,56 +660,152 @@ __global__ void k_gather_single(const uint32_t *list, uint64_t n, int N, uint64_
   lev_s[i] = lev[e];
   child_s[i] = child[e];
 }
-// Unit slot table of a group set.  Own slot l = xg + 3^g * sR: xg = sum_{d<g} x_d 3^d is the position in the
-// family's 3-point lattice of the grouped dimensions, sR the XOR-permuted rank bits of the others (lattice
-// bit s_d ^ c_d, the group's members share c_d for d >= g).  Slots LP.. (hanging groups): parent-lattice
-// rank (qG natural, tR ^ cR).  The table is padded to an even number of slots per unit.
-__global__ void k_unit_slots_group(const uint32_t *list, uint64_t nUnits, int dim, int g, int hang, uint64_t nReg, const uint32_t *e2n,
-                                   const uint32_t *pnode, const uint8_t *child, const uint8_t *lev, uint32_t *U, uint8_t *lev_g,
-                                   unsigned long long *fmask64)
+
+// ---- sibling families: unit slot tables ------------------------------------------------------
+// Lattice point k = sum_d p_d 3^d (p_d in 0..2) of family f: the node every child touching it stores at that
+// point, INVALID if they store none (a hanging point), bad[f] if the children disagree.
+__global__ void k_family_units(const uint32_t *mem, uint64_t nFam, int dim, const uint32_t *e2n, uint32_t *U, uint32_t *hm, uint32_t *bad)
 {
-  const int N = 1 << dim, NC = 1 << g, NR = 1 << (dim - g);
-  int L3 = 1;
-  for (int d = 0; d < g; d++) L3 *= 3;
-  const int LP = L3 * NR, spu = (LP + (hang ? N : 0) + 1) & ~1;
+  const int L = fam_L(dim), N = 1 << dim;
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= nUnits * spu) return;
-  const uint64_t u = i / spu;
-  const int q = (int)(i % spu);
-  const uint32_t *m = list + u * NC;
-  const int cR = child[m[0]] >> g;
+  if (i >= nFam * L) return;
+  const uint64_t f = i / L;
+  const int k = (int)(i % L);
+  int pd[4] = {0, 0, 0, 0};
+  for (int d = 0, kk = k; d < dim; d++, kk /= 3) pd[d] = kk % 3;
   uint32_t key = INVALID;
-  if (q < LP)
+  bool first = true, ok = true;
+  for (int c = 0; c < N; c++)
   {
-    const int xg = q % L3, sR = q / L3;
-    for (int cG = 0; cG < NC; cG++)
+    int r = 0;
+    bool touches = true;
+    for (int d = 0; d < dim; d++)
     {
-      int rG = 0, rem = xg;
-      bool ok = true;
-      for (int d = 0; d < g; d++)
-      {
-        const int r = (rem % 3) - ((cG >> d) & 1);
-        rem /= 3;
-        if (r < 0 || r > 1) ok = false;
-        else rG |= r << d;
-      }
-      if (!ok) continue;
-      const uint32_t k = e2n[(uint64_t)m[cG] * N + (rG | ((sR ^ cR) << g))];
-      if (k != INVALID) key = k;
+      const int rd = pd[d] - ((c >> d) & 1);
+      if (rd < 0 || rd > 1) touches = false;
+      else r |= rd << d;
     }
-  }
-  else if (q < LP + (hang ? N : 0))
-  {
-    const int t = q - LP;
-    const int pr = (t & (NC - 1)) | (((t >> g) ^ cR) << g);
-    for (int cG = 0; cG < NC; cG++)
-      if (m[cG] >= nReg) { key = pnode[((uint64_t)m[cG] - nReg) * N + pr]; break; }
+    if (!touches) continue;
+    const uint32_t v = e2n[(uint64_t)mem[f * N + c] * N + r];
+    if (first) { key = v; first = false; }
+    else if (v != key) ok = false;
   }
   U[i] = key;
-  if (q == 0) lev_g[u] = lev[m[0]];
-  if (hang && q < LP && key != INVALID) atomicOr(fmask64 + u, 1ull << q);
+  if (!ok) atomicOr(bad + f, 1u);
+  if (key == INVALID) atomicOr(hm + f * 4 + k / 27, 1u << (k % 27));
 }
 
+// Admits a family to the family kernel iff the lattice form of the hanging-node treatment equals the reference's
+// per-element one (FEM/include/matvec.h:403-522) on it.  Per element the reference (a) interpolates every unfilled
+// rank r of child c from the parent nodes q that are valid (level == L-1, matvec.h:417), (b) after the elemental
+// operator adds sum_{r unfilled} A^T[q, r] eout_c[r] to parent node q - but only if the CHILD's own rank q is unfilled
+// (quirk Q1, matvec.h:517).  On the family lattice (child c, rank r <-> point c + r; parent rank q <-> corner 2q):
+//   * the weight of corner q for point p is 2^-|odd(p)| if q is a corner of G(p), the smallest face of the parent cell
+//     that contains p (odd(p) = coordinates equal to 1), else 0 - independent of the child;
+//   * child c's rank q is the point p' = c + q, which lies in the closure of G(p) for every hanging p of c that
+//     gives q a non-zero weight, and is a corner of it only for q == c.
+// So if (C1) every non-corner point of closed G(p) hangs whenever p hangs, Q1 drops exactly the terms with q == c,
+// i.e. one scalar tau_c = sum_{r unfilled} 2^-|odd(c + r)| eout_c[r] per child, taken off its corner node, and the rest
+// is the plain transposed interpolation of the SUMMED lattice.  (C1) holds on 2:1-balanced trees without
+// domain-boundary hanging nodes (classes A/B of SURVEY 8a): p hangs on a coarser leaf E, closed G(p) lies in E's
+// boundary, and a point of E's boundary that is not a corner of E carries no node.  Also checked: (C2) hanging points
+// are neither corners nor the centre, (C3) for every hanging p, every child c touching it and every corner q of G(p)
+// the reference's pnode[c][q] is valid and IS the lattice's corner node.  Families that fail (class P trees, quirks
+// Q2/Q3) stay on the per-element sets.
+__global__ void k_family_check(const uint32_t *mem, uint64_t nFam, int dim, uint64_t nReg, const uint32_t *pnode, const uint32_t *U,
+                               const uint32_t *hm, uint32_t *bad)
+{
+  const int L = fam_L(dim), N = 1 << dim;
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nFam * L) return;
+  const uint64_t f = i / L;
+  const int k = (int)(i % L);
+  if (!((hm[f * 4 + k / 27] >> (k % 27)) & 1u)) return;
+  int pd[4] = {0, 0, 0, 0}, p3[4] = {1, 3, 9, 27};
+  int odd = 0, nodd = 0;
+  for (int d = 0, kk = k; d < dim; d++, kk /= 3)
+  {
+    pd[d] = kk % 3;
+    if (pd[d] == 1) { odd |= 1 << d; nodd++; }
+  }
+  bool ok = nodd >= 1 && nodd < dim;  // (C2)
+  // (C1): the points of closed G(p): odd coordinates range over 0..2
+  int npts = 1;
+  for (int j = 0; j < nodd; j++) npts *= 3;
+  for (int t = 0; t < npts && ok; t++)
+  {
+    int kk = 0, tt = t, no = 0;
+    for (int d = 0; d < dim; d++)
+    {
+      int x = pd[d];
+      if ((odd >> d) & 1) { x = tt % 3; tt /= 3; }
+      if (x == 1) no++;
+      kk += x * p3[d];
+    }
+    if (no == 0) { if (U[f * L + kk] == INVALID) ok = false; }                 // its corners are nodes
+    else if (!((hm[f * 4 + kk / 27] >> (kk % 27)) & 1u)) ok = false;         // everything else hangs
+  }
+  // (C3)
+  for (int c = 0; c < N && ok; c++)
+  {
+    bool touches = true;
+    for (int d = 0; d < dim; d++)
+    {
+      const int rd = pd[d] - ((c >> d) & 1);
+      if (rd < 0 || rd > 1) touches = false;
+    }
+    if (!touches) continue;
+    const uint32_t e = mem[f * N + c];
+    if (e < nReg) { ok = false; break; }  // a child with an unfilled rank is in the hanging list
+    for (int sub = 0; sub < (1 << nodd) && ok; sub++)
+    {
+      int q = 0, kc = 0, j = 0;
+      for (int d = 0; d < dim; d++)
+      {
+        int qd = pd[d] >> 1;
+        if ((odd >> d) & 1) { qd = (sub >> j) & 1; j++; }
+        q |= qd << d;
+        kc += 2 * qd * p3[d];
+      }
+      if (pnode[((uint64_t)e - nReg) * N + q] != U[f * L + kc]) ok = false;
+    }
+  }
+  if (!ok) atomicOr(bad + f, 1u);
+}
+
+// class of a family: 255 not admitted, else bit 0 = boundary (one member touches a ghost node; partitioned DA with overlap);
+// infam[e] = 1 for the members of admitted families
+__global__ void k_family_class(const uint32_t *mem, const uint32_t *bad, uint64_t nFam, int dim, uint64_t nReg, uint64_t nRegInt,
+                               uint64_t nHangInt, int phased, uint8_t *cls, uint8_t *infam)
+{
+  uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (f >= nFam) return;
+  if (bad[f]) { cls[f] = 255; return; }
+  const int N = 1 << dim;
+  int c = 0;
+  for (int t = 0; t < N; t++)
+  {
+    const uint32_t e = mem[f * N + t];
+    c |= elem_class(e, nReg, nRegInt, nHangInt, phased) & 1;
+    infam[e] = 1;
+  }
+  cls[f] = (uint8_t)c;
+}
+// unit slot table, per-family records {hanging masks x3, level} of the selected families, in family order
+__global__ void k_family_gather(const uint64_t *flag, const uint64_t *pos, uint64_t nFam, int dim, const uint32_t *mem, const uint8_t *lev,
+                                const uint32_t *Uall, const uint32_t *hm, uint32_t *U, uint32_t *frec)
+{
+  const int L = fam_L(dim);
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nFam * L) return;
+  const uint64_t f = i / L;
+  const int k = (int)(i % L);
+  if (!flag[f]) return;
+  const uint64_t u = pos[f];
+  U[u * L + k] = Uall[i];
+  if (k < 3) frec[u * 4 + k] = hm[f * 4 + k];
+  if (k == 3) frec[u * 4 + 3] = lev[mem[f << dim]];
+}
 static int scan_total(DA &da, const uint64_t *flag, uint64_t *pos, uint64_t n, uint64_t &total)
 {
   int rc = device_exclusive_scan(da, flag, pos, n + 1);
@@ -740,12 +821,12 @@ struct PendingSet
 };
 
 // per-element set over contiguous per-element arrays (the DA's own, or compact copies of the ungrouped elements)
-static int add_elem_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *e2n, const uint32_t *pnode, const uint8_t *lev,
+static int add_elem_set(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingSet> &pend, const uint32_t *e2n, const uint32_t *pnode, const uint8_t *lev,
                         const uint8_t *child, const uint32_t *fmask, uint64_t n, int rows, int phase, uint64_t elem0, uint64_t hang0)
 {
   if (n == 0) return DKT_OK;
-  da.sets.emplace_back();
-  ChunkSet &cs = da.sets.back();
+  sets.emplace_back();
+  ChunkSet &cs = sets.back();
   cs.rows = rows; cs.phase = phase; cs.elem0 = elem0; cs.hang0 = hang0; cs.nElem = n; cs.kind = 0;
   cs.xorperm = da.order == 1 ? 1 : 0;
   cs.spu = rows * da.N;
@@ -755,39 +836,35 @@ static int add_elem_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *e
   CK(cudaMalloc((void **)&U, n * cs.spu * sizeof(uint32_t)));
   DKT_LAUNCH(k_unit_slots_elem, nblk(n * cs.spu), 256, 0, da.stream)(e2n, pnode, child, n, da.N, rows, cs.xorperm, U);
   g_launches++;
-  pend.push_back({da.sets.size() - 1, U});
+  pend.push_back({sets.size() - 1, U});
   return DKT_OK;
 }
 
-static int add_group_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *list, uint64_t n, int g, int hang, int phase)
+// family set: units [a, b) of the gathered unit slot table / records of one class
+static int add_family_set(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingSet> &pend, const uint32_t *U, const uint32_t *frec, uint64_t n,
+                          int phase)
 {
   if (n == 0) return DKT_OK;
-  da.sets.emplace_back();
-  ChunkSet &cs = da.sets.back();
-  int L3 = 1;
-  for (int d = 0; d < g; d++) L3 *= 3;
-  const int LP = L3 << (da.dim - g);
-  cs.rows = hang ? 2 : 1; cs.phase = phase; cs.nElem = n; cs.kind = 1; cs.g = g; cs.xorperm = 1;
-  cs.spu = (LP + (hang ? da.N : 0) + 1) & ~1;
-  cs.elemsPerChunk = grp_upc(cs.spu, da.dim, g);
-  uint32_t *U = nullptr;
-  uint8_t *lev_g = nullptr;
-  unsigned long long *fm = nullptr;
-  CK(cudaMalloc((void **)&U, n * cs.spu * sizeof(uint32_t)));
-  CK(cudaMalloc((void **)&lev_g, n));
-  CK(cudaMalloc((void **)&fm, n * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(fm, 0, n * sizeof(unsigned long long), da.stream));
-  DKT_LAUNCH(k_unit_slots_group, nblk(n * cs.spu), 256, 0, da.stream)(list, n, da.dim, g, hang, da.nReg, da.d_e2n, da.d_pnode, da.d_mv_child,
-                                                                        da.d_mv_lev, U, lev_g, fm);
-  g_launches++;
-  cs.lev = lev_g; cs.fmask64 = (const uint64_t *)fm;
-  cs.owned.push_back(lev_g); cs.owned.push_back(fm);
-  pend.push_back({da.sets.size() - 1, U});
+  sets.emplace_back();
+  ChunkSet &cs = sets.back();
+  cs.rows = 1; cs.phase = phase; cs.nElem = n; cs.kind = 2; cs.xorperm = 0;
+  cs.spu = fam_L(da.dim);
+  cs.elemsPerChunk = fam_UPC(da.dim);
+  const uint32_t nChunks = (uint32_t)((n + cs.elemsPerChunk - 1) / cs.elemsPerChunk);
+  uint32_t *Uc = nullptr;
+  CK(cudaMalloc((void **)&Uc, n * cs.spu * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(Uc, U, n * cs.spu * sizeof(uint32_t), cudaMemcpyDeviceToDevice, da.stream));
+  // records padded to whole chunks: the kernel copies them chunk by chunk
+  CK(cudaMalloc((void **)&cs.d_frec, (size_t)nChunks * cs.elemsPerChunk * 4 * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(cs.d_frec, 0, (size_t)nChunks * cs.elemsPerChunk * 4 * sizeof(uint32_t), da.stream));
+  CK(cudaMemcpyAsync(cs.d_frec, frec, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, da.stream));
+  pend.push_back({sets.size() - 1, Uc});
   return DKT_OK;
 }
 
 // per-element set of the elements in `list` (outside complete families): compact copies of their rows
-static int add_single_set(DA &da, std::vector<PendingSet> &pend, const uint32_t *list, uint64_t nS, int hang, int phase)
+static int add_single_set(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingSet> &pend, const uint32_t *list, uint64_t nS, int hang,
+                          int phase)
 {
   if (nS == 0) return DKT_OK;
   const int N = da.N;
@@ -806,10 +883,10 @@ static int add_single_set(DA &da, std::vector<PendingSet> &pend, const uint32_t 
     DKT_LAUNCH(k_fmask, nblk(nS), 256, 0, da.stream)(e2n_s, child_s, nS, N, da.order == 1 ? 1 : 0, fm_s);
     g_launches++;
   }
-  int rc = add_elem_set(da, pend, e2n_s, pnode_s, lev_s, child_s, fm_s, nS, hang ? 2 : 1, phase, 0, 0);
+  int rc = add_elem_set(da, sets, pend, e2n_s, pnode_s, lev_s, child_s, fm_s, nS, hang ? 2 : 1, phase, 0, 0);
   if (rc == DKT_OK)
   {
-    ChunkSet &cs = da.sets.back();
+    ChunkSet &cs = sets.back();
     cs.owned.push_back(lev_s); cs.owned.push_back(child_s);
     if (fm_s) cs.owned.push_back(fm_s);
   }
@@ -819,176 +896,23 @@ static int add_single_set(DA &da, std::vector<PendingSet> &pend, const uint32_t 
   return rc;
 }
 
-// DKT_GROUPS=g: group the leaves of complete sibling families (see the file header).  0 / unset: off.
-// "g" or "gR,gH" (gH <= gR): regular groups of 2^gR leaves; groups of that size with a hanging member are split into
-// groups of 2^gH leaves, which are regular or hanging in their turn (smaller hanging groups need fewer registers).
-static bool group_kernel_exists(int dim, int g)
+// order 1: sibling-family sets unless DKT_FAMILIES=0
+static bool families_wanted(const DA &da)
 {
-  return (dim == 4 && g >= 1 && g <= 3) || (dim == 3 && (g == 2 || g == 3)) || (dim == 2 && g == 2);
-}
-static int groups_requested(const DA &da, int &gH)
-{
-  gH = 0;
-  const char *e = getenv("DKT_GROUPS");
-  if (!e) return 0;
-  const int g = atoi(e);
-  gH = g;
-  if (const char *c = strchr(e, ',')) gH = atoi(c + 1);
-  if (g <= 0 || da.order != 1 || gH <= 0 || gH > g) return 0;
-  if (!group_kernel_exists(da.dim, g) || !group_kernel_exists(da.dim, gH)) return 0;
-  return g;
+  if (da.order != 1) return false;
+  const char *e = getenv("DKT_FAMILIES");
+  return !(e && atoi(e) == 0);
 }
 
-int build_chunks(DA &da)
+// writing references of every node over all sets of a collection, then the chunk tables
+static int finish_sets(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingSet> &pend, int rc)
 {
-  // more than 27 nodes per element (4-D order 2): no shared-memory kernel; every matvec runs on the flat kernels
-  if (da.N > MAX_NPE) return DKT_OK;
-  if (da.nNodes >= 0x7FFFFFFFull) { set_error("more than 2^31 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
-  if (getenv("DKT_GROUPS") && da.nNodes >= 0x3FFFFFFFull) { set_error("DKT_GROUPS: more than 2^30 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
-  CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
-  DKT_LAUNCH(k_child_numbers, nblk(da.nMv), 256, 0, da.stream)(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth, da.d_mv_child);
-  g_launches++;
-  const int N = da.N;
-  const int xorperm = da.order == 1 ? 1 : 0;
-  if (da.nHang)
-  {
-    CK(cudaMalloc((void **)&da.d_fmask, da.nHang * sizeof(uint32_t)));
-    DKT_LAUNCH(k_fmask, nblk(da.nHang), 256, 0, da.stream)(da.d_e2n + da.nReg * (uint64_t)N, da.d_mv_child + da.nReg, da.nHang, N, xorperm,
-                                                           da.d_fmask);
-    g_launches++;
-  }
-  std::vector<PendingSet> pend;
-  int rc = DKT_OK;
-  int gHang = 0;
-  const int g = groups_requested(da, gHang);
-  da.groups = g;
-  if (!g)
-  {
-    // element ranges: one regular + one hanging set, or (partitioned) three phases of each:
-    // interior first half / boundary / interior second half - see run_matvec_dist
-    struct Range { uint64_t a, b; int phase; };
-    std::vector<Range> rr, hr;
-    if (da.phased)
-    {
-      const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
-      rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
-      hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
-    }
-    else
-    {
-      rr = {{0, da.nReg, 0}};
-      hr = {{0, da.nHang, 0}};
-    }
-    for (const Range &r : rr)
-      if (rc == DKT_OK && r.b > r.a)
-        rc = add_elem_set(da, pend, da.d_e2n + r.a * N, nullptr, da.d_mv_lev + r.a, da.d_mv_child + r.a, nullptr, r.b - r.a, 1, r.phase, r.a, 0);
-    for (const Range &r : hr)
-      if (rc == DKT_OK && r.b > r.a)
-        rc = add_elem_set(da, pend, da.d_e2n + (da.nReg + r.a) * N, da.d_pnode + r.a * N, da.d_mv_lev + da.nReg + r.a,
-                          da.d_mv_child + da.nReg + r.a, da.d_fmask + r.a, r.b - r.a, 2, r.phase, da.nReg + r.a, r.a);
-  }
-  else
-  {
-    const uint64_t n = da.nMv;
-    const int nch = 1 << da.dim;
-    const int phased = da.phased ? 1 : 0;
-    uint32_t *inv = nullptr, *mem = nullptr;
-    uint64_t *flag = nullptr, *pos = nullptr;
-    uint8_t *infam = nullptr, *cls = nullptr;
-    CK(cudaMalloc((void **)&inv, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&flag, (n + 1) * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&pos, (n + 1) * sizeof(uint64_t)));
-    CK(cudaMalloc((void **)&infam, std::max<uint64_t>(n, 1)));
-    CK(cudaMalloc((void **)&cls, std::max<uint64_t>(n, 1)));
-    CK(cudaMemsetAsync(infam, 0, std::max<uint64_t>(n, 1), da.stream));
-    DKT_LAUNCH(k_invert_src, nblk(n), 256, 0, da.stream)(da.d_mv_src, n, da.mv_src0, inv);
-    DKT_LAUNCH(k_family_heads, nblk(n + 1), 256, 0, da.stream)(inv, da.d_mv_xyz, da.d_mv_lev, n, da.dim, da.max_depth, flag);
-    g_launches += 2;
-    uint64_t nFam = 0;
-    rc = scan_total(da, flag, pos, n, nFam);
-    if (rc) return rc;
-    CK(cudaMalloc((void **)&mem, std::max<uint64_t>(nFam, 1) * nch * sizeof(uint32_t)));
-    DKT_LAUNCH(k_family_members, nblk(n), 256, 0, da.stream)(inv, flag, pos, da.d_mv_child, n, da.dim, mem, infam);
-    g_launches++;
-    std::vector<uint32_t *> lists;  // freed after the unit slot tables are built
-    // interior units run in two halves around the boundary ones (see run_matvec_dist); unpartitioned: one set
-    auto add_sets = [&](const uint32_t *list, uint64_t cnt, int width, int c, int gsz) -> int {
-      const int hang = (c >> 1) & 1, bdy = c & 1;
-      struct Sub { uint64_t a, b; int phase; };
-      std::vector<Sub> subs;
-      if (!phased) subs = {{0, cnt, 0}};
-      else if (bdy) subs = {{0, cnt, 1}};
-      else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
-      for (const Sub &s : subs)
-      {
-        const int r = gsz ? add_group_set(da, pend, list + s.a * width, s.b - s.a, gsz, hang, s.phase)
-                          : add_single_set(da, pend, list + s.a, s.b - s.a, hang, s.phase);
-        if (r) return r;
-      }
-      return DKT_OK;
-    };
-    // groups by class: regular / hanging x interior / boundary; with DKT_GROUPS=gR,gH a second pass makes the
-    // smaller groups out of the size-2^gR groups that have a hanging member
-    for (int pass = 0; pass < (gHang < g ? 2 : 1) && rc == DKT_OK; pass++)
-    {
-      const int gp = pass == 0 ? g : gHang;
-      const int mode = gHang < g ? pass + 1 : 0;
-      const int NCp = 1 << gp;
-      const uint64_t nGroups = nFam << (da.dim - gp);
-      if (!nGroups) continue;
-      uint64_t *gflag = nullptr, *gpos = nullptr;
-      uint8_t *gcls = nullptr;
-      CK(cudaMalloc((void **)&gflag, (nGroups + 1) * sizeof(uint64_t)));
-      CK(cudaMalloc((void **)&gpos, (nGroups + 1) * sizeof(uint64_t)));
-      CK(cudaMalloc((void **)&gcls, nGroups));
-      DKT_LAUNCH(k_group_class, nblk(nGroups), 256, 0, da.stream)(mem, nGroups, da.dim, gp, g, mode, da.nReg, da.nRegInterior,
-                                                                  da.nHangInterior, phased, gcls);
-      g_launches++;
-      for (int c = 0; c < 4 && rc == DKT_OK; c++)
-      {
-        DKT_LAUNCH(k_class_flags, nblk(nGroups + 1), 256, 0, da.stream)(gcls, nGroups, c, gflag);
-        g_launches++;
-        uint64_t cnt = 0;
-        rc = scan_total(da, gflag, gpos, nGroups, cnt);
-        if (rc || !cnt) continue;
-        uint32_t *list = nullptr;
-        CK(cudaMalloc((void **)&list, cnt * NCp * sizeof(uint32_t)));
-        lists.push_back(list);
-        DKT_LAUNCH(k_group_list, nblk(nGroups), 256, 0, da.stream)(mem, gflag, gpos, nGroups, da.dim, gp, list);
-        g_launches++;
-        rc = add_sets(list, cnt, NCp, c, gp);
-      }
-      CK(cudaStreamSynchronize(da.stream));
-      cudaFree(gflag); cudaFree(gpos); cudaFree(gcls);
-    }
-    // the elements outside complete families, by the same classes
-    DKT_LAUNCH(k_single_class, nblk(n), 256, 0, da.stream)(infam, n, da.nReg, da.nRegInterior, da.nHangInterior, phased, cls);
-    g_launches++;
-    for (int c = 0; c < 4 && rc == DKT_OK; c++)
-    {
-      DKT_LAUNCH(k_class_flags, nblk(n + 1), 256, 0, da.stream)(cls, n, c, flag);
-      g_launches++;
-      uint64_t cnt = 0;
-      rc = scan_total(da, flag, pos, n, cnt);
-      if (rc || !cnt) continue;
-      uint32_t *list = nullptr;
-      CK(cudaMalloc((void **)&list, cnt * sizeof(uint32_t)));
-      lists.push_back(list);
-      DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
-      g_launches++;
-      rc = add_sets(list, cnt, 1, c, 0);
-    }
-    CK(cudaStreamSynchronize(da.stream));
-    for (uint32_t *l : lists) cudaFree(l);
-    cudaFree(inv); cudaFree(mem); cudaFree(flag); cudaFree(pos); cudaFree(infam); cudaFree(cls);
-  }
-  // writing references of every node over all sets, then the chunk tables
   uint32_t *refcnt = nullptr;
   CK(cudaMalloc((void **)&refcnt, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t)));
   CK(cudaMemsetAsync(refcnt, 0, std::max<uint64_t>(da.nNodes, 1) * sizeof(uint32_t), da.stream));
   for (const PendingSet &ps : pend)
   {
-    const ChunkSet &cs = da.sets[ps.idx];
+    const ChunkSet &cs = sets[ps.idx];
     const uint64_t ns = cs.nElem * cs.spu;
     if (rc == DKT_OK && ns)
     {
@@ -997,10 +921,161 @@ int build_chunks(DA &da)
     }
   }
   for (const PendingSet &ps : pend)
-    if (rc == DKT_OK) rc = build_set(da, da.sets[ps.idx], ps.U, refcnt);
+    if (rc == DKT_OK) rc = build_set(da, sets[ps.idx], ps.U, refcnt);
   cudaStreamSynchronize(da.stream);
   for (const PendingSet &ps : pend) cudaFree(ps.U);
   cudaFree(refcnt);
+  return rc;
+}
+
+// per-element sets of all visited elements: one regular + one hanging set, or (partitioned) three phases of each:
+// interior first half / boundary / interior second half - see run_matvec_dist
+static int build_elem_sets(DA &da, std::vector<ChunkSet> &sets)
+{
+  const int N = da.N;
+  std::vector<PendingSet> pend;
+  int rc = DKT_OK;
+  struct Range { uint64_t a, b; int phase; };
+  std::vector<Range> rr, hr;
+  if (da.phased)
+  {
+    const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
+    rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
+    hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
+  }
+  else
+  {
+    rr = {{0, da.nReg, 0}};
+    hr = {{0, da.nHang, 0}};
+  }
+  for (const Range &r : rr)
+    if (rc == DKT_OK && r.b > r.a)
+      rc = add_elem_set(da, sets, pend, da.d_e2n + r.a * N, nullptr, da.d_mv_lev + r.a, da.d_mv_child + r.a, nullptr, r.b - r.a, 1, r.phase, r.a, 0);
+  for (const Range &r : hr)
+    if (rc == DKT_OK && r.b > r.a)
+      rc = add_elem_set(da, sets, pend, da.d_e2n + (da.nReg + r.a) * N, da.d_pnode + r.a * N, da.d_mv_lev + da.nReg + r.a,
+                        da.d_mv_child + da.nReg + r.a, da.d_fmask + r.a, r.b - r.a, 2, r.phase, da.nReg + r.a, r.a);
+  return finish_sets(da, sets, pend, rc);
+}
+
+// family sets of the admitted complete families + per-element sets of everything else
+static int build_family_sets(DA &da, std::vector<ChunkSet> &sets)
+{
+  const uint64_t n = da.nMv;
+  const int nch = 1 << da.dim, L = fam_L(da.dim);
+  const int phased = da.phased ? 1 : 0;
+  std::vector<PendingSet> pend;
+  int rc = DKT_OK;
+  uint32_t *inv = nullptr, *mem = nullptr, *Uall = nullptr, *hm = nullptr, *bad = nullptr;
+  uint64_t *flag = nullptr, *pos = nullptr;
+  uint8_t *infam = nullptr, *cls = nullptr, *fcls = nullptr;
+  CK(cudaMalloc((void **)&inv, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&flag, (n + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&pos, (n + 1) * sizeof(uint64_t)));
+  CK(cudaMalloc((void **)&infam, std::max<uint64_t>(n, 1)));
+  CK(cudaMalloc((void **)&cls, std::max<uint64_t>(n, 1)));
+  CK(cudaMemsetAsync(infam, 0, std::max<uint64_t>(n, 1), da.stream));
+  DKT_LAUNCH(k_invert_src, nblk(n), 256, 0, da.stream)(da.d_mv_src, n, da.mv_src0, inv);
+  DKT_LAUNCH(k_family_heads, nblk(n + 1), 256, 0, da.stream)(inv, da.d_mv_xyz, da.d_mv_lev, n, da.dim, da.max_depth, flag);
+  g_launches += 2;
+  uint64_t nFam = 0;
+  rc = scan_total(da, flag, pos, n, nFam);
+  if (rc) return rc;
+  std::vector<void *> temps;  // freed after the unit slot tables are built
+  if (nFam)
+  {
+    CK(cudaMalloc((void **)&mem, nFam * nch * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&Uall, nFam * L * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&hm, nFam * 4 * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&bad, nFam * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&fcls, nFam));
+    CK(cudaMemsetAsync(hm, 0, nFam * 4 * sizeof(uint32_t), da.stream));
+    CK(cudaMemsetAsync(bad, 0, nFam * sizeof(uint32_t), da.stream));
+    DKT_LAUNCH(k_family_members, nblk(n), 256, 0, da.stream)(inv, flag, pos, da.d_mv_child, n, da.dim, mem);
+    DKT_LAUNCH(k_family_units, nblk(nFam * L), 256, 0, da.stream)(mem, nFam, da.dim, da.d_e2n, Uall, hm, bad);
+    DKT_LAUNCH(k_family_check, nblk(nFam * L), 256, 0, da.stream)(mem, nFam, da.dim, da.nReg, da.d_pnode, Uall, hm, bad);
+    DKT_LAUNCH(k_family_class, nblk(nFam), 256, 0, da.stream)(mem, bad, nFam, da.dim, da.nReg, da.nRegInterior, da.nHangInterior, phased, fcls,
+                                                              infam);
+    g_launches += 4;
+    uint64_t *fflag = nullptr, *fpos = nullptr;
+    CK(cudaMalloc((void **)&fflag, (nFam + 1) * sizeof(uint64_t)));
+    CK(cudaMalloc((void **)&fpos, (nFam + 1) * sizeof(uint64_t)));
+    for (int c = 0; c < 2 && rc == DKT_OK; c++)
+    {
+      DKT_LAUNCH(k_class_flags, nblk(nFam + 1), 256, 0, da.stream)(fcls, nFam, c, fflag);
+      g_launches++;
+      uint64_t cnt = 0;
+      rc = scan_total(da, fflag, fpos, nFam, cnt);
+      if (rc || !cnt) continue;
+      uint32_t *Uc = nullptr, *frec = nullptr;
+      CK(cudaMalloc((void **)&Uc, cnt * L * sizeof(uint32_t)));
+      CK(cudaMalloc((void **)&frec, cnt * 4 * sizeof(uint32_t)));
+      temps.push_back(Uc);
+      temps.push_back(frec);
+      DKT_LAUNCH(k_family_gather, nblk(nFam * L), 256, 0, da.stream)(fflag, fpos, nFam, da.dim, mem, da.d_mv_lev, Uall, hm, Uc, frec);
+      g_launches++;
+      // interior families run in two halves around the boundary ones (see run_matvec_dist); unpartitioned: one set
+      struct Sub { uint64_t a, b; int phase; };
+      std::vector<Sub> subs;
+      if (!phased) subs = {{0, cnt, 0}};
+      else if (c == 1) subs = {{0, cnt, 1}};
+      else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
+      for (const Sub &sb : subs)
+        if (rc == DKT_OK) rc = add_family_set(da, sets, pend, Uc + sb.a * L, frec + sb.a * 4, sb.b - sb.a, sb.phase);
+    }
+    CK(cudaStreamSynchronize(da.stream));
+    cudaFree(fflag);
+    cudaFree(fpos);
+  }
+  // the elements outside admitted families, by class: regular / hanging x interior / boundary
+  DKT_LAUNCH(k_single_class, nblk(n), 256, 0, da.stream)(infam, n, da.nReg, da.nRegInterior, da.nHangInterior, phased, cls);
+  g_launches++;
+  for (int c = 0; c < 4 && rc == DKT_OK; c++)
+  {
+    DKT_LAUNCH(k_class_flags, nblk(n + 1), 256, 0, da.stream)(cls, n, c, flag);
+    g_launches++;
+    uint64_t cnt = 0;
+    rc = scan_total(da, flag, pos, n, cnt);
+    if (rc || !cnt) continue;
+    uint32_t *list = nullptr;
+    CK(cudaMalloc((void **)&list, cnt * sizeof(uint32_t)));
+    temps.push_back(list);
+    DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
+    g_launches++;
+    const int hang = (c >> 1) & 1, bdy = c & 1;
+    struct Sub { uint64_t a, b; int phase; };
+    std::vector<Sub> subs;
+    if (!phased) subs = {{0, cnt, 0}};
+    else if (bdy) subs = {{0, cnt, 1}};
+    else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
+    for (const Sub &sb : subs)
+      if (rc == DKT_OK) rc = add_single_set(da, sets, pend, list + sb.a, sb.b - sb.a, hang, sb.phase);
+  }
+  CK(cudaStreamSynchronize(da.stream));
+  for (void *t : temps) cudaFree(t);
+  cudaFree(inv); cudaFree(mem); cudaFree(Uall); cudaFree(hm); cudaFree(bad); cudaFree(flag); cudaFree(pos); cudaFree(infam); cudaFree(cls);
+  cudaFree(fcls);
+  return finish_sets(da, sets, pend, rc);
+}
+
+int build_chunks(DA &da)
+{
+  // more than 27 nodes per element (4-D order 2): no shared-memory kernel; every matvec runs on the flat kernels
+  if (da.N > MAX_NPE) return DKT_OK;
+  if (da.nNodes >= 0x3FFFFFFFull) { set_error("more than 2^30 nodes on one rank"); return DKT_ERR_UNSUPPORTED; }
+  CK(cudaMalloc((void **)&da.d_mv_child, std::max<uint64_t>(da.nMv, 1)));
+  DKT_LAUNCH(k_child_numbers, nblk(da.nMv), 256, 0, da.stream)(da.d_mv_xyz, da.d_mv_lev, da.nMv, da.dim, da.max_depth, da.d_mv_child);
+  g_launches++;
+  if (da.nHang)
+  {
+    CK(cudaMalloc((void **)&da.d_fmask, da.nHang * sizeof(uint32_t)));
+    DKT_LAUNCH(k_fmask, nblk(da.nHang), 256, 0, da.stream)(da.d_e2n + da.nReg * (uint64_t)da.N, da.d_mv_child + da.nReg, da.nHang, da.N,
+                                                           da.order == 1 ? 1 : 0, da.d_fmask);
+    g_launches++;
+  }
+  da.families = families_wanted(da);
+  int rc = da.families ? build_family_sets(da, da.sets) : build_elem_sets(da, da.sets);
+  if (rc) return rc;
   int dev = 0;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&da.numSMs, cudaDevAttrMultiProcessorCount, dev));
@@ -1015,9 +1090,14 @@ int build_chunks(DA &da)
       CK(cudaEventCreateWithFlags(&da.ev_join[a], cudaEventDisableTiming));
     }
   }
-  return rc;
+  return DKT_OK;
 }
-
+// the per-element tables of a DA that runs on family sets, for the operators k_mvf does not serve
+static int ensure_elem_sets(DA &da)
+{
+  if (!da.families || !da.sets_elem.empty() || da.nMv == 0) return DKT_OK;
+  return build_elem_sets(da, da.sets_elem);
+}
 // ------------------------------------------------------------------------------------------
 // matvec kernels
 // ------------------------------------------------------------------------------------------
@@ -1036,9 +1116,6 @@ struct Mv3Params
   const uint8_t *lev;    // level of the set's elements
   const uint8_t *child;  // Morton child numbers of the set's elements
   const uint32_t *fmask; // hanging set: filled own slots (slot order)
-  const uint32_t *rk16, *ps16;   // group sets: 16-bit node ranks / positions, two slots per word
-  const uint32_t *rec;           // group sets: gid | boundary bit 30 | shared bit 31 per chunk node
-  const uint64_t *fmask64;       // hanging group sets: filled own lattice slots
   uint32_t nSet, nChunks, elemsPerChunk, xcap, ncap, jdStride;
   int q1mask;
   int exact_ip;          // order 1: ip0/ip1 equal the exact interpolation to 1e-13
@@ -1472,459 +1549,364 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
   g_launches++;
   return DKT_OK;
 }
-
 // ------------------------------------------------------------------------------------------
-// sibling-group kernel (order 1, identity / Walsh-Hadamard operators, exact interpolation)
+// sibling-family kernel (order 1, identity / Walsh-Hadamard operators, exact interpolation)
 // ------------------------------------------------------------------------------------------
-// One thread per GROUP: the 2^G leaves of a complete sibling family that share the child-number bits of the
-// dimensions >= G.  Their nodes form a 3^G x 2^(DIM-G) lattice (LP slots; the dimensions >= G keep the XOR
-// schedule, so the 2^(DIM-G) groups of a family still read the same node in the same instruction).  Per group:
-// LP gathers, 2^G elemental operators on register-resident values with STATIC indices, LP scatters; a hanging
-// group additionally reads the 2^DIM parent nodes once, interpolates them to the whole lattice (exact order-1
-// interpolation: midpoints) and scatters one masked transposed sum.  Quirk Q1 (FEM/include/matvec.h:517) is
-// applied per child at run time from the 64-bit fill mask, so every parent slot is a writing slot here.
-// Pipeline per chunk (two barriers): the 4-byte node records are staged in shared memory by cp.async - every
-// thread copies, consumes and later overwrites only its OWN records -, the gather of chunk i+1 is issued right
-// after barrier A and stays in flight during the whole of chunk i.
-template <int DIM, int G>
-struct Grp
+// One CTA per chunk of UPC families (512 elements), 128 threads, no loop over chunks: 3-4 CTAs share an SM and
+// overlap each other's memory and compute phases.
+//   L0  thread 0: cp.async.bulk (TMA 1-D bulk copies, mbarrier completion) of the chunk's contiguous tables - node
+//       records, rk16, inv16, family records, jd|cnt - into shared memory
+//   L1  all threads, once the records are there: cp.async 8-byte gathers un[n] <- u[gid[n]]           -- barrier A
+//   F   warp-local (a warp owns FPW families in every phase up to Q): thread per lattice slot,
+//       Ls[f][p] = lscale(level f) * un[rk16[slot]]; a hanging point takes the mean of the corners of G(p) instead
+//       (exact order-1 interpolation from the parent's nodes = the family's corners)                  -- __syncwarp
+//   Q   thread per QUAD (the 4 children differing in dimensions 0, 1; the quads of a family are neighbouring lanes):
+//       per child 2^dim conflict-free LDS with static offsets, the elemental operator (identity or Walsh-Hadamard
+//       form; dimensions >= 2 are addressed XOR-permuted, with which both commute), Q1's scalar tau_c off its corner,
+//       accumulation into the quad's 9 * 2^(dim-2) lattice points in registers; the points shared with the other
+//       quads are summed with 1-2 shuffles each; in a family with hanging points the transposed interpolation then
+//       runs on the registers, one dimension at a time (each lane owns the corner side of its XOR-permuted
+//       dimensions, so no further communication); __syncwarp; the sums go back to Ls in place      -- barrier B
+//   N   thread per chunk node: acc = sum_k Ls[inv16[jd[k] + n]], one plain store (node private to the chunk)
+//       or one fp64 RED
+struct MvfParams
 {
-  static constexpr int N = 1 << DIM, NC = 1 << G, NR = 1 << (DIM - G);
-  static constexpr int L3 = (G == 1 ? 3 : G == 2 ? 9 : G == 3 ? 27 : 81);
-  static constexpr int LP = L3 * NR;
-  // lattice slot of rank r (grouped bits natural, the others XOR-permuted) of child cG
-  __host__ __device__ static constexpr int lat(int cG, int r)
-  {
-    int xg = 0, p3 = 1;
-    for (int d = 0; d < G; d++)
-    {
-      xg += (((cG >> d) & 1) + ((r >> d) & 1)) * p3;
-      p3 *= 3;
-    }
-    return xg + L3 * (r >> G);
-  }
-  // the lattice slots of child cG as a bit mask
-  __host__ __device__ static constexpr unsigned long long child_mask(int cG)
-  {
-    unsigned long long m = 0;
-    for (int r = 0; r < N; r++) m |= 1ull << lat(cG, r);
-    return m;
-  }
-  // child cG is the first (smallest) child touching the lattice point of its rank r
-  __host__ __device__ static constexpr bool first(int cG, int r) { return ((cG & ~r) & (NC - 1)) == 0; }
+  const double *in;
+  double *out;
+  const uint16_t *rk16, *inv16, *jd;
+  const uint32_t *frec, *rec, *nloc;
+  const uint64_t *node_off;
+  uint32_t nSet, nChunks, jdStride, ncap;  // ncap: multiple of 4, >= the largest chunk's padded node count
+  double lscale[32];
+  double K[16];  // Walsh-Hadamard form: diagonal / N
 };
 
-// parent values (index: grouped bits natural | other bits already interpolated) -> lattice, one grouped dimension
-// at a time: src index a + 3^K * b (b's lowest bit = parent corner along dimension K), dst index a + 3^K * x + 3^(K+1) * (b >> 1)
-template <int DIM, int G, int K>
-__device__ __forceinline__ void grp_expand(const double *src, double *dst)
+#ifndef DKT_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-  constexpr int P3 = (K == 0 ? 1 : K == 1 ? 3 : K == 2 ? 9 : 27);
-  constexpr int NB = 1 << (DIM - K - 1);
-#pragma unroll
-  for (int b = 0; b < NB; b++)
-#pragma unroll
-    for (int a = 0; a < P3; a++)
-    {
-      const double lo = src[a + P3 * (2 * b)], hi = src[a + P3 * (2 * b + 1)];
-      dst[a + 3 * P3 * b] = lo;
-      dst[a + P3 + 3 * P3 * b] = 0.5 * (lo + hi);
-      dst[a + 2 * P3 + 3 * P3 * b] = hi;
-    }
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+}
+#else
+// emulation: the barrier word counts [expected bytes + 1 | completed bytes]; a waiting fiber lets the others run
+inline void mbar_init(uint64_t *bar, int) { *bar = 0; }
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += (uint64_t)bytes + 1; }
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  memcpy(dst, src, bytes);
+  *bar += (uint64_t)bytes << 32;
+}
+inline void mbar_wait(uint64_t *bar, uint32_t)
+{
+  while ((uint32_t)*bar == 0 || (*bar >> 32) + 1 < (uint32_t)*bar) emu::spin_yield();
+}
+#endif
 
-// butterflies of the strides LO, 2 LO, .. < HI
-template <int N, int LO, int HI>
-__device__ __forceinline__ void wht_range(double *v)
+// shared-memory layout of k_mvf (bytes; every section a multiple of 16)
+template <int DIM>
+struct FamSmem
 {
-#pragma unroll
-  for (int s = LO; s < HI; s <<= 1)
+  using F = Fam<DIM>;
+  uint32_t oUn, oRec, oRk, oInv, oFrec, oJd, oBar, total;
+  __host__ __device__ FamSmem(uint32_t ncap, uint32_t jdStride)
   {
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      if (i & s) continue;
-      const double a = v[i], b = v[i + s];
-      v[i] = a + b;
-      v[i + s] = a - b;
-    }
+    uint32_t o = F::UPC * F::S * 8;
+    oUn = o; o += (ncap + 2) * 8;
+    oRec = o; o += ncap * 4;
+    oRk = o; o += F::UPC * F::L * 2;
+    oInv = o; o += F::UPC * F::L * 2;
+    oFrec = o; o += F::UPC * 16;
+    oJd = o; o += 2 * jdStride * 2;
+    oBar = o; o += 16;
+    total = o;
   }
-}
-// Walsh-Hadamard butterflies along the XOR-permuted dimensions (>= G) of a group lattice, index xg + 3^G * sR
-template <int DIM, int G>
-__device__ __forceinline__ void grp_wht_lattice(double *v)
-{
-  using GP = Grp<DIM, G>;
-#pragma unroll
-  for (int k = 0; k < DIM - G; k++)
-  {
-    const int st = GP::L3 << k;
-#pragma unroll
-    for (int l = 0; l < GP::LP; l++)
-    {
-      if ((l / st) & 1) continue;
-      const double a = v[l], b = v[l + st];
-      v[l] = a + b;
-      v[l + st] = a - b;
-    }
-  }
-}
+};
 
-template <int DIM, int G, int OPKIND, bool DIRI, bool HANG, int TPB>
-__global__ void __launch_bounds__(TPB, HANG ? DKT_GRP_MINB_HANG : DKT_GRP_MINB_REG) k_mvg(const __grid_constant__ Mv3Params<DIM, 1> p)
+template <int DIM, int OPKIND, bool DIRI>
+__global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __grid_constant__ MvfParams p)
 {
-  using GP = Grp<DIM, G>;
-  constexpr int N = GP::N, LP = GP::LP, NC = GP::NC;
-  constexpr int SPU = (LP + (HANG ? N : 0) + 1) & ~1;
-  constexpr int NW = SPU / 2;
+  using F = Fam<DIM>;
+  constexpr int L = F::L, S = F::S, SA = F::SA, SB = F::SB, N = F::N, NS = F::NS, NL = F::NL, QPF = F::QPF, FPW = F::FPW, UPC = F::UPC,
+                TPB = F::TPB;
+  static_assert((UPC * S * 8) % 16 == 0 && (UPC * L * 2) % 16 == 0, "bulk copies need 16-byte sections");
   DKT_DYN_SMEM(double, sm);
-  double *X = sm;                                      // [xcap]
-  double *unb = sm + p.xcap;                           // [2][ncap]
-  int *jdb = (int *)(sm + p.xcap + 2 * p.ncap);        // [2][jd[jdStride] | cnt[jdStride]]
-  uint32_t *recb = (uint32_t *)(jdb + 4 * p.jdStride); // [2][ncap]
+  const FamSmem<DIM> lay(p.ncap, p.jdStride);
+  char *smc = (char *)sm;
+  double *Ls = sm;
+  double *un = (double *)(smc + lay.oUn);
+  uint32_t *rec = (uint32_t *)(smc + lay.oRec);
+  uint16_t *rk = (uint16_t *)(smc + lay.oRk);
+  uint16_t *inv = (uint16_t *)(smc + lay.oInv);
+  uint32_t *frec = (uint32_t *)(smc + lay.oFrec);
+  uint16_t *jd = (uint16_t *)(smc + lay.oJd);
+  uint64_t *bar = (uint64_t *)(smc + lay.oBar);
 
-  const int tid = threadIdx.x;
-  const uint32_t E = p.elemsPerChunk;
-  uint64_t c = blockIdx.x;
-  if (c >= p.nChunks) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t c = blockIdx.x;
+  const uint32_t u0 = c * UPC;
+  const int nfam = (int)min((uint32_t)UPC, p.nSet - u0);
+  const uint64_t noff = p.node_off[c];
+  const int nloc = (int)p.nloc[c];
+  const uint32_t recBytes = (uint32_t)((nloc + 3) & ~3) * 4u;
 
-  auto issue_rec = [&](uint64_t oa, int nloc, int b) {
-    uint32_t *dst = recb + b * p.ncap;
-    for (int n = tid; n < nloc; n += TPB) cp_async4(dst + n, p.rec + oa + n);
-  };
-  auto issue_gather = [&](uint64_t cc, int nloc, int b) {
-    double *un = unb + b * p.ncap;
-    const uint32_t *rec = recb + b * p.ncap;
-    if (tid == 0) un[nloc] = 0.0;  // the entry absent nodes read
-    for (int n = tid; n < nloc; n += TPB)
-    {
-      const uint32_t r = rec[n];
-      if (DIRI && (r & REC_BDY)) un[n] = 0.0;
-      else cp_async8(un + n, p.in + (r & REC_GID));
-    }
-    int *jdn = jdb + b * 2 * p.jdStride;
-    for (int k = tid; k < 2 * (int)p.jdStride; k += TPB) jdn[k] = p.jd[cc * (uint64_t)(2 * p.jdStride) + k];
-  };
-  uint32_t wr[NW];
-  int levU = 0;
-  uint64_t fm = 0;
-  auto load_ranks = [&](uint64_t cc) {
-    const uint64_t u0 = cc * (uint64_t)E;
-    const int nu = (int)min((uint64_t)E, (uint64_t)p.nSet - u0);
-    if (tid < nu)
-    {
-      const uint32_t *sw = p.rk16 + u0 * NW + tid;
-#pragma unroll
-      for (int j = 0; j < NW; j++) wr[j] = sw[(uint32_t)j * E];
-      levU = p.lev[u0 + tid];
-      if (HANG) fm = p.fmask64[u0 + tid];
-    }
-  };
-#define GRK(l) ((wr[(l) >> 1] >> (((l) & 1) * 16)) & 0xFFFFu)
-#define GPS(l) ((ps[(l) >> 1] >> (((l) & 1) * 16)) & 0xFFFFu)
-
-  // ---- prologue ---------------------------------------------------------------------------------
-  const uint64_t stride = gridDim.x;
-  uint64_t oa = p.node_off[c], ob = p.node_off[c + 1];
-  int nlocC = (int)(ob - oa);
-  issue_rec(oa, nlocC, 0);
+  // ---- L0: bulk copies of the chunk's tables
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+    mbar_expect_tx(bar, recBytes);
+    bulk_g2s(rec, p.rec + noff, recBytes, bar);
+    const uint32_t slotBytes = UPC * L * 2, frecBytes = UPC * 16, jdBytes = 2 * p.jdStride * 2;
+    mbar_expect_tx(bar + 1, 2 * slotBytes + frecBytes + jdBytes);
+    bulk_g2s(rk, p.rk16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
+    bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
+    bulk_g2s(frec, p.frec + (uint64_t)c * (UPC * 4), frecBytes, bar + 1);
+    bulk_g2s(jd, p.jd + (uint64_t)c * (2 * p.jdStride), jdBytes, bar + 1);
+  }
+  // ---- L1: gather the chunk's node values
+  mbar_wait(bar, 0);
+  for (int n = tid; n < nloc; n += TPB)
+  {
+    const uint32_t r = rec[n];
+    if (DIRI && (r & REC_BDY)) un[n] = 0.0;
+    else cp_async8(un + n, p.in + (r & REC_GID));
+  }
+  if (tid == 0) un[nloc] = 0.0;  // what the slots without a node read
   cp_async_commit();
+  mbar_wait(bar + 1, 0);
   cp_async_wait_all();
-  issue_gather(c, nlocC, 0);
-  uint64_t cn = c + stride;
-  bool hasN = cn < p.nChunks;
-  int nlocN = 0;
-  if (hasN)
-  {
-    const uint64_t a = p.node_off[cn], b = p.node_off[cn + 1];
-    nlocN = (int)(b - a);
-    issue_rec(a, nlocN, 1);
-  }
-  cp_async_commit();
-  load_ranks(c);
-  int buf = 0;
+  __syncthreads();  // A
 
-  while (true)
+  const int fw0 = warp * FPW;
+  const int nfw = min(FPW, nfam - fw0);  // families of this warp
+  if (nfw > 0)
   {
-    double *un = unb + buf * p.ncap;
-    const int *jd = jdb + buf * 2 * p.jdStride;
-    cp_async_wait_all();
-    __syncthreads();  // A: un/jd of this chunk visible, own records of the next chunk landed; X and un[buf^1] free
-    const uint64_t cnn = cn + stride;
-    const bool hasNN = hasN && cnn < p.nChunks;
-    uint64_t oaNN = 0;
-    int nlocNN = 0;
-    if (hasN)
+    // ---- F: fill the lattices of the warp's families
+    for (int i = lane; i < nfw * L; i += 32)
     {
-      issue_gather(cn, nlocN, buf ^ 1);
-      if (hasNN)
+      const int fl = i / L, k = i - fl * L, f = fw0 + fl;
+      const uint16_t *rkf = rk + f * L;
+      const uint32_t *fr = frec + f * 4;
+      double v;
+      if (!((fr[k / 27] >> (k % 27)) & 1u)) v = un[rkf[k]];
+      else
       {
-        oaNN = p.node_off[cnn];
-        nlocNN = (int)(p.node_off[cnn + 1] - oaNN);
+        // a hanging point: mean of the corners of the smallest face of the parent cell that contains it
+        int st[DIM];
+        int m = 0;
+        for (int d = 0, kk = k, p3 = 1; d < DIM; d++, kk /= 3, p3 *= 3)
+          if (kk % 3 == 1) st[m++] = p3;
+        v = 0.0;
+        for (int sub = 0; sub < (1 << m); sub++)
+        {
+          int kc = k;
+          for (int j = 0; j < m; j++) kc += ((sub >> j) & 1) ? st[j] : -st[j];
+          v += un[rkf[kc]];
+        }
+        v *= 1.0 / (double)(1 << m);
+      }
+      if (OPKIND != DKT_OP_IDENTITY) v *= p.lscale[fr[3] & 31u];
+      Ls[f * S + fam_laddr(DIM, k)] = v;
+    }
+    __syncwarp();
+
+    // ---- Q: one quad per thread
+    const int fl = lane / QPF, j = lane % QPF;
+    const bool act = fl < nfw;
+    const int f = fw0 + (act ? fl : 0);
+    const int c2 = j & 1, c3 = (j >> 1) & 1;
+    double *Lf = Ls + f * S;
+    const uint32_t *fr = frec + f * 4;
+    int boff[NS];        // where the quad's points with (s2, s3) start; s_d = 0: the corner side 2 c_d, s_d = 1: the middle
+    uint32_t g[NS];      // their hanging bits (bit i0 + 3 i1)
+#pragma unroll
+    for (int sg = 0; sg < NS; sg++)
+    {
+      const int s2 = sg & 1, s3 = sg >> 1;
+      const int p2 = NL >= 1 ? (s2 ? 1 : 2 * c2) : 0, p3 = NL >= 2 ? (s3 ? 1 : 2 * c3) : 0;
+      boff[sg] = SA * p2 + SB * p3;
+      g[sg] = (fr[DIM == 4 ? p3 : 0] >> (9 * p2)) & 0x1FFu;
+    }
+    const bool hangfam = act && (fr[0] | fr[1] | fr[2]) != 0u;
+    double acc[9 * NS];
+#pragma unroll
+    for (int cq = 0; cq < 4; cq++)
+    {
+      const int c0 = cq & 1, c1 = cq >> 1;
+      double e[N];
+#pragma unroll
+      for (int r = 0; r < N; r++) e[r] = Lf[boff[r >> 2] + (c0 + (r & 1)) + 3 * (c1 + ((r >> 1) & 1))];
+      if (OPKIND == OP_HADAMARD)
+      {
+        wht<N>(e);
+#pragma unroll
+        for (int i = 0; i < N; i++) e[i] *= p.K[i];
+        wht<N>(e);
+      }
+      if (hangfam)
+      {
+        // quirk Q1 on a family (see k_family_check): tau = sum over the child's hanging ranks of 2^-|odd| eout, off its corner
+        double tau = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; r++)
+        {
+          const int i0 = c0 + (r & 1), i1 = c1 + ((r >> 1) & 1), sg = r >> 2;
+          const int nodd = (i0 == 1) + (i1 == 1) + (sg & 1) + (sg >> 1);
+          if (nodd == 0) continue;  // the corner itself
+          const double w = 1.0 / (double)(1 << nodd);
+          if ((g[sg] >> (i0 + 3 * i1)) & 1u) tau = fma(w, e[r], tau);
+        }
+        e[c0 | (c1 << 1)] -= tau;
+      }
+#pragma unroll
+      for (int r = 0; r < N; r++)
+      {
+        const int r0 = r & 1, r1 = (r >> 1) & 1;
+        const int a = (c0 + r0) + 3 * (c1 + r1) + 9 * (r >> 2);
+        if ((c0 == 0 || r0 == 1) && (c1 == 0 || r1 == 1)) acc[a] = e[r];  // first child that touches the point
+        else acc[a] += e[r];
       }
     }
-    cp_async_commit();
-    // ---- T2: the groups of this chunk
-    {
-      const uint64_t u0 = c * (uint64_t)E;
-      const int nu = (int)min((uint64_t)E, (uint64_t)p.nSet - u0);
-      if (tid < nu)
+    // the middle points of the lane dimensions are shared with the neighbouring quads
+#pragma unroll
+    for (int sg = 1; sg < NS; sg++)
+#pragma unroll
+      for (int i = 0; i < 9; i++)
       {
-        uint32_t ps[NW];
+        double v = acc[i + 9 * sg];
+        if (sg & 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (sg & 2) v += __shfl_xor_sync(0xffffffffu, v, 2);
+        acc[i + 9 * sg] = v;
+      }
+    if (hangfam)
+    {
+      // transposed interpolation of the hanging points towards the corners, one dimension at a time
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i1 = 0; i1 < 3; i1++)
+          if ((g[sg] >> (1 + 3 * i1)) & 1u)
+          {
+            const double h = 0.5 * acc[1 + 3 * i1 + 9 * sg];
+            acc[0 + 3 * i1 + 9 * sg] += h;
+            acc[2 + 3 * i1 + 9 * sg] += h;
+          }
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i0 = 0; i0 < 3; i0++)
+          if ((g[sg] >> (i0 + 3)) & 1u)
+          {
+            const double h = 0.5 * acc[i0 + 3 + 9 * sg];
+            acc[i0 + 9 * sg] += h;
+            acc[i0 + 6 + 9 * sg] += h;
+          }
+#pragma unroll
+      for (int d = 0; d < NL; d++)
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
         {
-          const uint32_t *sw = p.ps16 + u0 * NW + tid;
+          if (!((sg >> d) & 1)) continue;
 #pragma unroll
-          for (int j = 0; j < NW; j++) ps[j] = sw[(uint32_t)j * E];
+          for (int i = 0; i < 9; i++)
+            if ((g[sg] >> i) & 1u) acc[i + 9 * (sg ^ (1 << d))] += 0.5 * acc[i + 9 * sg];
         }
-        const double s = p.lscale[levU];
-        double v[LP], o[LP];
-        if (!HANG)
-        {
+    }
+    __syncwarp();  // every lane of the warp has read its lattice points
+    if (act)
+    {
 #pragma unroll
-          for (int l = 0; l < LP; l++) v[l] = un[GRK(l)];
-          // Walsh-Hadamard form: the butterflies along the XOR-permuted dimensions are the same for every child of the
-          // group, so they run ONCE on the lattice (forward here, backward on the summed output); the children then only
-          // transform along the grouped dimensions.  (H D H commutes with the XOR permutation: its signs in the
-          // frequency domain cancel around the diagonal D.)
-          constexpr bool RSHARE = (OPKIND == OP_HADAMARD) && (DKT_GRP_RSHARE != 0) && (G < DIM);
-          if (RSHARE) grp_wht_lattice<DIM, G>(v);
+      for (int sg = 0; sg < NS; sg++)
+      {
+        // a shared point is stored by the quad with c_d == 0
+        if (((sg & 1) && c2) || ((sg & 2) && c3)) continue;
 #pragma unroll
-          for (int cG = 0; cG < NC; cG++)
-          {
-            double e[N];
-#pragma unroll
-            for (int r = 0; r < N; r++) e[r] = v[GP::lat(cG, r)];
-            if (OPKIND == OP_HADAMARD)
-            {
-              wht_range<N, 1, (RSHARE ? NC : N)>(e);
-#pragma unroll
-              for (int i = 0; i < N; i++) e[i] *= p.K[i] * s;
-              wht_range<N, 1, (RSHARE ? NC : N)>(e);
-            }
-#pragma unroll
-            for (int r = 0; r < N; r++)
-            {
-              if (GP::first(cG, r)) o[GP::lat(cG, r)] = e[r];
-              else o[GP::lat(cG, r)] += e[r];
-            }
-          }
-          if (RSHARE) grp_wht_lattice<DIM, G>(o);
-#pragma unroll
-          for (int l = 0; l < LP; l++) X[GPS(l)] = o[l];
-        }
-        else
-        {
-          {
-            // parent nodes -> whole lattice: subset sums along the XOR-permuted dimensions, midpoints along the grouped ones
-            double par[N];
-#pragma unroll
-            for (int t = 0; t < N; t++) par[t] = un[GRK(LP + t)];
-#pragma unroll
-            for (int b = NC; b < N; b <<= 1)
-#pragma unroll
-              for (int i = 0; i < N; i++)
-              {
-                if (i & b) continue;
-                par[i | b] = 0.5 * (par[i] + par[i | b]);
-              }
-            if constexpr (G == 1) grp_expand<DIM, G, 0>(par, v);
-            else if constexpr (G == 2)
-            {
-              double t1[3 * (N / 2)];
-              grp_expand<DIM, G, 0>(par, t1);
-              grp_expand<DIM, G, 1>(t1, v);
-            }
-            else
-            {
-              static_assert(G <= 3, "grouped dimensions");
-              double t1[3 * (N / 2)], t2[9 * (N / 4)];
-              grp_expand<DIM, G, 0>(par, t1);
-              grp_expand<DIM, G, 1>(t1, t2);
-              grp_expand<DIM, G, 2>(t2, v);
-            }
-          }
-#pragma unroll
-          for (int l = 0; l < LP; l++)
-          {
-            const double own = un[GRK(l)];
-            if ((fm >> l) & 1ull) v[l] = own;
-          }
-          double ta[N];
-#pragma unroll
-          for (int q = 0; q < N; q++) ta[q] = 0.0;
-#pragma unroll
-          for (int cG = 0; cG < NC; cG++)
-          {
-            double e[N];
-#pragma unroll
-            for (int r = 0; r < N; r++) e[r] = v[GP::lat(cG, r)];
-            if (OPKIND == OP_HADAMARD)
-            {
-              wht<N>(e);
-#pragma unroll
-              for (int i = 0; i < N; i++) e[i] *= p.K[i] * s;
-              wht<N>(e);
-            }
-#pragma unroll
-            for (int r = 0; r < N; r++)
-            {
-              if (GP::first(cG, r)) o[GP::lat(cG, r)] = e[r];
-              else o[GP::lat(cG, r)] += e[r];
-            }
-            // a child without hanging nodes sends nothing to the parent nodes.  Neighbouring groups hang on the same
-            // coarse face, so the branch is mostly warp-uniform.
-            if ((~fm & GP::child_mask(cG)) == 0ull) continue;
-#pragma unroll
-            for (int r = 0; r < N; r++)
-              if ((fm >> GP::lat(cG, r)) & 1ull) e[r] = 0.0;  // nullify prior to back-interpolation (matvec.h:497-499)
-            // transposed interpolation of this child: A0^T along permuted dimensions and grouped ones with bit 0, A1^T otherwise
-#pragma unroll
-            for (int d = 0; d < DIM; d++)
-            {
-              const int b = 1 << d;
-              const bool a1 = (d < G) && ((cG >> d) & 1);
-#pragma unroll
-              for (int i = 0; i < N; i++)
-              {
-                if (i & b) continue;
-                if (!a1)
-                {
-                  const double h = 0.5 * e[i | b];
-                  e[i] += h;
-                  e[i | b] = h;
-                }
-                else
-                {
-                  const double h = 0.5 * e[i];
-                  e[i | b] += h;
-                  e[i] = h;
-                }
-              }
-            }
-            // quirk Q1: the LEAF's fill flag of rank q masks the contribution to the PARENT's rank q (matvec.h:517)
-#pragma unroll
-            for (int q = 0; q < N; q++)
-            {
-              ta[q] += ((fm >> GP::lat(cG, q)) & 1ull) ? 0.0 : e[q];
-            }
-          }
-#pragma unroll
-          for (int l = 0; l < LP; l++) X[GPS(l)] = o[l];
-#pragma unroll
-          for (int t = 0; t < N; t++) X[GPS(LP + t)] = ta[t];
-        }
+        for (int i = 0; i < 9; i++) Lf[boff[sg] + i] = acc[i + 9 * sg];
       }
     }
-    if (hasN) load_ranks(cn);
-    __syncthreads();  // B: X complete
-    // ---- T4: own nodes of this chunk
-    {
-      // four nodes per thread at a time: independent accumulation chains, one jd[j] / cnt[j] load for the four.  Nodes
-      // are ranked by run length (descending) and cnt[j] = #nodes with a run longer than j, so node n has a j-th
-      // contribution iff n < cnt[j]; nodes >= cnt[0] are only read by this chunk.
-      const uint32_t *rec = recb + buf * p.ncap;
-      const int *cnt = jd + p.jdStride;
-      const int cnt0 = cnt[0];
-      for (int base = tid; base < cnt0; base += 4 * TPB)
-      {
-        uint32_t r[4];
-        double acc[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          const int n = base + i * TPB;
-          r[i] = 0u;
-          acc[i] = 0.0;
-          if (n < cnt0)
-          {
-            r[i] = rec[n];
-            acc[i] = X[n];  // jd[0] == 0
-          }
-        }
-        for (int j = 1; base < cnt[j]; j++)
-        {
-          const int off = jd[j] + base, cj = cnt[j];
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if (base + i * TPB < cj) acc[i] += X[off + i * TPB];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          if (base + i * TPB >= cnt0) continue;
-          if (DIRI && (r[i] & REC_BDY)) continue;
-          if (r[i] & REC_SHARED) atomicAdd(p.out + (r[i] & REC_GID), acc[i]);
-          else p.out[r[i] & REC_GID] = acc[i];
-        }
-      }
-    }
-    if (!hasN) break;
-    if (hasNN) issue_rec(oaNN, nlocNN, buf);  // own records of the chunk after the next one
-    cp_async_commit();
-    c = cn;
-    cn = cnn;
-    hasN = hasNN;
-    nlocC = nlocN;
-    nlocN = nlocNN;
-    buf ^= 1;
   }
-#undef GRK
-#undef GPS
+  __syncthreads();  // B
+
+  // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
+  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.
+  {
+    const uint16_t *cnt = jd + p.jdStride;
+    const int cnt0 = cnt[0];
+    for (int n = tid; n < cnt0; n += TPB)
+    {
+      double a = Ls[inv[n]];  // jd[0] == 0
+      for (int k = 1; n < (int)cnt[k]; k++) a += Ls[inv[(int)jd[k] + n]];
+      const uint32_t r = rec[n];
+      if (DIRI && (r & REC_BDY)) continue;
+      if (r & REC_SHARED) atomicAdd(p.out + (r & REC_GID), a);
+      else p.out[r & REC_GID] = a;
+    }
+  }
 }
 
-template <int DIM, int G, int OPKIND, bool DIRI, bool HANG>
-static int launch_group_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, 1> &p)
+template <int DIM, int OPKIND, bool DIRI>
+static int launch_family_one(DA &da, const ChunkSet &cs, MvfParams &p)
 {
-  using GP = Grp<DIM, G>;
-  constexpr int SPU = (GP::LP + (HANG ? GP::N : 0) + 1) & ~1;
-  constexpr int TPB = grp_tpb(SPU, DIM, G);
-  if (cs.spu != SPU || (int)cs.elemsPerChunk > TPB) { set_error("internal: group set does not match its kernel"); return DKT_ERR_INVALID; }
-  p.rk16 = (const uint32_t *)cs.d_rk16; p.ps16 = (const uint32_t *)cs.d_ps16; p.rec = (const uint32_t *)cs.d_rec; p.jd = cs.d_jd;
-  p.node_off = cs.d_node_off; p.lev = cs.lev; p.fmask64 = cs.fmask64;
-  p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.elemsPerChunk = cs.elemsPerChunk;
-  p.xcap = (uint32_t)cs.elemsPerChunk * SPU + 258u;  // + padding of the first 16 diagonals + the trash position
-  p.ncap = (cs.maxNloc + 2) & ~1u;
-  p.jdStride = cs.jdStride;
-  const size_t smem = ((size_t)p.xcap + 2 * (size_t)p.ncap) * sizeof(double) + 2 * (size_t)p.ncap * sizeof(uint32_t) +
-                      4 * (size_t)p.jdStride * sizeof(int);
-  auto kern = k_mvg<DIM, G, OPKIND, DIRI, HANG, TPB>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TPB, smem));
-  if (perSM < 1) { set_error("group kernel does not fit on an SM"); return DKT_ERR_CUDA; }
-  const uint32_t grid = std::min<uint32_t>(cs.nChunks, (uint32_t)(perSM * da.numSMs));
-  DKT_LAUNCH(kern, grid, TPB, smem, da.cur ? da.cur : da.stream)(p);
+  using F = Fam<DIM>;
+  if (cs.spu != F::L || (int)cs.elemsPerChunk != F::UPC) { set_error("internal: family set does not match its kernel"); return DKT_ERR_INVALID; }
+  p.rk16 = cs.d_rk16; p.inv16 = cs.d_inv16; p.jd = cs.d_jd; p.frec = cs.d_frec; p.rec = (const uint32_t *)cs.d_rec; p.nloc = cs.d_nloc;
+  p.node_off = cs.d_node_off;
+  p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.jdStride = cs.jdStride;
+  p.ncap = (cs.maxNloc + 3) & ~3u;
+  const FamSmem<DIM> lay(p.ncap, p.jdStride);
+  auto kern = k_mvf<DIM, OPKIND, DIRI>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  DKT_LAUNCH(kern, cs.nChunks, F::TPB, lay.total, da.cur ? da.cur : da.stream)(p);
   g_launches++;
   return DKT_OK;
 }
 
 template <int DIM, int ORDER, int OPKIND, bool DIRI>
-static int launch_group(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
+static int launch_family(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p3)
 {
   if constexpr (ORDER == 1 && (OPKIND == DKT_OP_IDENTITY || OPKIND == OP_HADAMARD))
   {
-    const bool hang = cs.rows == 2;
-#define GRP_CASE(D, GG)                                                                      \
-  if constexpr (DIM == D)                                                                    \
-  {                                                                                          \
-    if (cs.g == GG)                                                                          \
-      return hang ? launch_group_one<DIM, GG, OPKIND, DIRI, true>(da, cs, p)                 \
-                  : launch_group_one<DIM, GG, OPKIND, DIRI, false>(da, cs, p);               \
+    static thread_local MvfParams p;
+    p.in = p3.in;
+    p.out = p3.out;
+    for (int l = 0; l < 32; l++) p.lscale[l] = p3.lscale[l];
+    for (int i = 0; i < 16; i++) p.K[i] = i < (1 << DIM) ? p3.K[i] : 0.0;
+    return launch_family_one<DIM, OPKIND, DIRI>(da, cs, p);
   }
-    GRP_CASE(4, 1)
-    GRP_CASE(4, 2)
-    GRP_CASE(4, 3)
-    GRP_CASE(3, 2)
-    GRP_CASE(3, 3)
-    GRP_CASE(2, 2)
-#undef GRP_CASE
-  }
-  set_error("internal: no sibling-group kernel for this (dim, g, operator)");
+  set_error("internal: no sibling-family kernel for this (order, operator)");
   return DKT_ERR_UNSUPPORTED;
 }
 
 template <int DIM, int ORDER, int OPKIND, bool DIRI>
-static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
+static int launch_mv3(DA &da, const std::vector<ChunkSet> &sets, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int TPB_R = (N == 27) ? 160 : DKT_ROWS;  // >= elements per chunk (one element per thread)
@@ -1938,7 +1920,7 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
   // RED), so they may run side by side on n streams - small sets then fill the tails of the big ones
   const int ns = std::min(da.mvStreams, DA::MAX_AUX + 1);
   int k = 0, used = 0;
-  for (const ChunkSet &cs : da.sets)
+  for (const ChunkSet &cs : sets)
   {
     if (!cs.nChunks || !((phaseMask >> cs.phase) & 1u)) continue;
     int rc = DKT_OK;
@@ -1955,7 +1937,7 @@ static int launch_mv3(DA &da, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
       }
       k++;
     }
-    if (cs.kind == 1) rc = launch_group<DIM, ORDER, OPKIND, DIRI>(da, cs, p);
+    if (cs.kind == 2) rc = launch_family<DIM, ORDER, OPKIND, DIRI>(da, cs, p);
     else if (cs.rows == 1)
     {
       if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p);
@@ -2041,8 +2023,14 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
       }
     }
   }
-  if (da.groups && !((hadamard || op->kind == DKT_OP_IDENTITY) && p.exact_ip))
-    return run_matvec(da, op, d_in, d_out, scale, flags);  // group tables serve the fast forms only (DKT_GROUPS is opt-in)
+  // family tables serve the fast forms only; everything else runs on the per-element tables of all elements (built on first use)
+  const std::vector<ChunkSet> *sets = &da.sets;
+  if (da.families && !((hadamard || op->kind == DKT_OP_IDENTITY) && p.exact_ip))
+  {
+    const int rc = ensure_elem_sets(da);
+    if (rc) return rc;
+    sets = &da.sets_elem;
+  }
   if (zeroOut)
   {
     CK(cudaMemsetAsync(d_out, 0, da.nNodes * sizeof(double), da.stream));
@@ -2052,12 +2040,12 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
   if constexpr (ORDER == 1)
   {
     if (hadamard)
-      return diri ? launch_mv3<DIM, ORDER, OP_HADAMARD, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, OP_HADAMARD, false>(da, p, phaseMask);
+      return diri ? launch_mv3<DIM, ORDER, OP_HADAMARD, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, OP_HADAMARD, false>(da, *sets, p, phaseMask);
   }
   if (op->kind == DKT_OP_IDENTITY)
-    return diri ? launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, false>(da, p, phaseMask);
+    return diri ? launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, false>(da, *sets, p, phaseMask);
   if (op->kind == DKT_OP_DENSE)
-    return diri ? launch_mv3<DIM, ORDER, DKT_OP_DENSE, true>(da, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_DENSE, false>(da, p, phaseMask);
+    return diri ? launch_mv3<DIM, ORDER, DKT_OP_DENSE, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_DENSE, false>(da, *sets, p, phaseMask);
   set_error("unknown operator kind");
   return DKT_ERR_INVALID;
 }

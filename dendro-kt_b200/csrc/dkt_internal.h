@@ -51,12 +51,14 @@ struct ChunkSet
   const uint8_t *lev = nullptr;    // level
   const uint8_t *child = nullptr;  // per-element sets: Morton child number
   const uint32_t *fmask = nullptr; // hanging per-element sets: filled own slots
-  // sibling-group sets (kind == 1, see dkt_chunks.cu): one unit = 2^g leaves of a complete family
-  int kind = 0, g = 0;
-  int spu = 0;                     // slots per unit (padded to an even number for group sets)
-  uint16_t *d_rk16 = nullptr, *d_ps16 = nullptr;  // node rank / position of every slot, two slots per 32-bit word
+  // sibling-family sets (kind == 2, see dkt_chunks.cu): one unit = a complete family of 2^dim leaves with its 3^dim node lattice
+  int kind = 0;
+  int spu = 0;                     // slots per unit
+  uint16_t *d_rk16 = nullptr;      // [nChunks*upc*spu] node rank of every lattice slot (unit-major); nloc = no node (hanging point)
+  uint16_t *d_inv16 = nullptr;     // [nChunks*upc*spu] shared-memory lattice address of the contribution at jagged-diagonal position i
+  uint32_t *d_frec = nullptr;      // [nChunks*upc*4] per family: hanging-point masks (27 lattice points per word) x3, level
+  uint32_t *d_nloc = nullptr;      // [nChunks] nodes of every chunk (d_node_off is padded to multiples of 4 for the bulk copies)
   void *d_rec = nullptr;           // [totalNodes] uint32: gid | boundary bit 30 | shared bit 31 (d_jd then holds [jd | cnt] per chunk)
-  const uint64_t *fmask64 = nullptr; // hanging group sets: filled own lattice slots
   std::vector<void *> owned;       // device buffers freed with the set
 };
 
@@ -97,12 +99,16 @@ struct DA
 
   double ip[2][MAX_M * MAX_M];     // parent->child 1-D matrices, A[k*M+j]
 
-  std::vector<ChunkSet> sets;      // chunked tables; single rank: {regular, hanging}; partitioned: x3 phases
+  // chunked tables.  Order 1: {families, regular singles, hanging singles}; otherwise {regular, hanging}; partitioned: x3 phases
+  std::vector<ChunkSet> sets;
+  // order 1 with family sets: the per-element tables of ALL elements, built on first use by an operator the family
+  // kernel does not serve (general dense K_ref, caller-supplied interpolation)
+  std::vector<ChunkSet> sets_elem;
+  bool families = false;           // `sets` holds family sets
   // partitioned DA: regular elements are ordered [interior | boundary], boundary = touches a ghost node
   uint64_t nRegInterior = 0, nHangInterior = 0;
   bool phased = false;
   int commSMs = 0;                 // SMs left to the NCCL kernels during the interior phases
-  int groups = 0;                  // DKT_GROUPS=g at construction: sibling-group sets in use (order 1)
   // DKT_MV_STREAMS=n (opt-in): the chunk sets of one matvec call run on n streams (dkt_chunks.cu launch_mv3)
   static constexpr int MAX_AUX = 3;
   int mvStreams = 1;

@@ -39,7 +39,14 @@ static __global__ void k_p2p_signal(uint32_t *const *peer_flag, const uint64_t *
   __threadfence_system();
   *(volatile uint32_t *)peer_flag[p] = epoch;
 }
-// every block waits for the epoch of all peers that send to this rank (about 2 s at most, then *err = 1)
+// every block waits for the epoch of all peers that send to this rank.  A peer that stays away for ~30 s (6e10 cycles) is an
+// error: *err = 1 and the kernel traps, so the failure surfaces at the host's next synchronisation instead of stale data
+// flowing into the result.
+#ifdef DKT_EMU
+#define DKT_P2P_TRAP() abort()
+#else
+#define DKT_P2P_TRAP() __trap()
+#endif
 __device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, int *err)
 {
   const int p = threadIdx.x;
@@ -49,7 +56,12 @@ __device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const u
     while ((int32_t)(flags[p] - epoch) < 0)
     {
       __nanosleep(100);
-      if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1); break; }
+      if (clock64() - t0 > 60000000000ll)
+      {
+        atomicExch(err, 1);
+        __threadfence_system();
+        DKT_P2P_TRAP();
+      }
     }
     __threadfence_system();
   }

@@ -172,9 +172,10 @@ void *dkt_da_stream(dkt_da *da);
 /* Launch on the caller's stream from now on (e.g. torch's current stream); NULL restores the
  * DA's own stream.  The caller keeps the stream alive. */
 int dkt_da_set_stream(dkt_da *da, void *cuda_stream);
-/* Diagnostics of the chunked tables: out[0..4] = regular set {chunks, elements per chunk, max nodes per
- * chunk, max run length, total chunk nodes}, out[5..9] = the same for the hanging set. */
-int dkt_da_chunk_info(const dkt_da *da, uint64_t out[10]);
+/* Diagnostics of the chunked tables: out[0..4] = regular per-element sets {chunks, units per chunk, max nodes per
+ * chunk, max run length, total chunk nodes}, out[5..9] = the same for the hanging per-element sets, out[10..14] for
+ * the sibling-family sets (unit = family), out[15] = elements inside sibling families. */
+int dkt_da_chunk_info(const dkt_da *da, uint64_t out[16]);
 /* Number of kernels launched by this library in the calling process since load. */
 uint64_t dkt_kernel_launch_count(void);
 

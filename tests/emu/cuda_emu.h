@@ -168,6 +168,12 @@ template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o)
   while (x.read[partner] < gen) emu::spin_yield();
   return r;
 }
+// warp barrier: a butterfly of rendezvous (every lane has heard from every other lane after five rounds)
+inline void __syncwarp(unsigned m = 0xffffffffu)
+{
+  int x = 0;
+  for (int o = 1; o < 32; o <<= 1) x += __shfl_xor_sync(m, x, o);
+}
 inline void __threadfence_system() {}
 inline void __nanosleep(unsigned) {}
 inline long long clock64() { static long long c = 0; return c += 1000; }

@@ -2,7 +2,7 @@
 // library's own build_da + partition_da (dry run) + build_chunks, then the harness performs the ghost read / write-back
 // with the library's send and receive lists (what ncclSend/Recv or the peer-memory kernels do between GPUs) around the
 // library's phased chunk matvec.  Checks ownership, local numbering, exchange lists, the [interior | boundary] element
-// order and the phased chunk sets (per-element and sibling-group) on REAL partitions.
+// order and the phased chunk sets (sibling-family and per-element) on REAL partitions.
 #include "dkt_internal.h"
 #include "cuda_emu.h"
 

@@ -18,7 +18,7 @@ static T *dup(const T *src, size_t n)
 }
 
 
-// info: per set 8 numbers {kind, rows, g, units, chunks, units per chunk, max nodes per chunk, total chunk nodes}, up to 8 sets
+// info: per set 8 numbers {kind, rows, slots per unit, units, chunks, units per chunk, max nodes per chunk, total chunk nodes}, up to 8 sets
 extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint64_t nReg, uint64_t nNodes, const uint32_t *e2n,
                           const uint32_t *pnode, const uint32_t *mv_xyz, const uint8_t *mv_lev, const uint32_t *mv_src,
                           const uint8_t *isbdy, const double *ip0, const double *ip1, int op_kind, const double *kref, double alpha,
@@ -50,7 +50,7 @@ extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint6
     {
       if (k >= 16) break;
       uint64_t *o = info + 8 * k++;
-      o[0] = cs.kind; o[1] = cs.rows; o[2] = cs.g; o[3] = cs.nElem; o[4] = cs.nChunks; o[5] = cs.elemsPerChunk; o[6] = cs.maxNloc;
+      o[0] = cs.kind; o[1] = cs.rows; o[2] = cs.spu; o[3] = cs.nElem; o[4] = cs.nChunks; o[5] = cs.elemsPerChunk; o[6] = cs.maxNloc;
       o[7] = cs.totalNodes | ((uint64_t)cs.phase << 56);
     }
     dkt_op op;

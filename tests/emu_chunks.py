@@ -31,10 +31,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None, dirichlet=False, groups=0, flags=0, order=0,
+def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None, dirichlet=False, families=1, flags=0, order=0,
            phased_seed=None):
     """Emulated dkt chunk path on the oracle's FlatTables `t`.  Returns (v, sets) where sets lists
-    (kind, rows, g, units, chunks, units per chunk, max nodes per chunk, total chunk nodes, phase).
+    (kind, rows, slots per unit, units, chunks, units per chunk, max nodes per chunk, total chunk nodes, phase); kind 2 = sibling
+    families (families=0 builds per-element sets only, DKT_FAMILIES=0).
     phased_seed: emulate a partitioned DA with comm/compute overlap - a random third of the elements counts as
     "boundary", the lists are ordered [interior | boundary] like dkt_dist.cu does, visit positions get an offset,
     and the three phases run one after the other."""
@@ -71,8 +72,8 @@ def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None,
     u = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
     out = np.full(nNodes, np.nan)
     info = np.zeros(128, dtype=np.uint64)
-    old = {k: os.environ.get(k) for k in ("DKT_GROUPS", "DKT_EMU_ORDER")}
-    os.environ["DKT_GROUPS"] = str(groups)
+    old = {k: os.environ.get(k) for k in ("DKT_FAMILIES", "DKT_EMU_ORDER")}
+    os.environ["DKT_FAMILIES"] = str(families)
     os.environ["DKT_EMU_ORDER"] = str(order)
     try:
         L = lib()

@@ -39,9 +39,9 @@ def _p(a):
 
 
 class EmuDA:
-    """dkt.DA's construction and matvec, emulated.  groups: DKT_GROUPS spec for the chunk tables."""
+    """dkt.DA's construction and matvec, emulated.  families: DKT_FAMILIES (0: per-element chunk tables only)."""
 
-    def __init__(self, xyz, lev, dim, order, max_depth, sfc=0, ip0=None, ip1=None, groups="0", flags=0):
+    def __init__(self, xyz, lev, dim, order, max_depth, sfc=0, ip0=None, ip1=None, families=1, flags=0):
         import flat
         L = lib()
         xyz = np.ascontiguousarray(xyz, dtype=np.uint32)
@@ -50,15 +50,15 @@ class EmuDA:
             ip0, ip1 = flat.default_interp(order)
         ip0 = np.ascontiguousarray(np.asarray(ip0, dtype=np.float64).ravel())
         ip1 = np.ascontiguousarray(np.asarray(ip1, dtype=np.float64).ravel())
-        old = os.environ.get("DKT_GROUPS")
-        os.environ["DKT_GROUPS"] = str(groups)
+        old = os.environ.get("DKT_FAMILIES")
+        os.environ["DKT_FAMILIES"] = str(families)
         try:
             self._h = L.emu_da_create(dim, order, max_depth, sfc, _p(xyz), _p(lev), len(lev), _p(ip0), _p(ip1), flags)
         finally:
             if old is None:
-                os.environ.pop("DKT_GROUPS", None)
+                os.environ.pop("DKT_FAMILIES", None)
             else:
-                os.environ["DKT_GROUPS"] = old
+                os.environ["DKT_FAMILIES"] = old
         if not self._h:
             raise RuntimeError("emu_da_create: " + L.emu_last_error().decode())
         s = np.zeros(16, dtype=np.uint64)

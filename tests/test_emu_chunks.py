@@ -1,8 +1,8 @@
 """CPU tests of the chunked matvec's LOGIC: dendro-kt_b200/csrc/dkt_chunks.cu is compiled with g++ against
 tests/emu/cuda_emu.h (threads of a block = fibers, see there) and its table construction + kernels are run on
 the oracle's element->node tables, then compared with the golden vectors taken from the reference and with the
-oracle.  This covers the per-element sets (the production default) and the opt-in sibling-group sets
-(DKT_GROUPS) without a GPU; it says nothing about performance and is not a CPU path of the product."""
+oracle.  This covers the sibling-family sets (the order-1 default) and the per-element sets (DKT_FAMILIES=0, order 2,
+general operators) without a GPU; it says nothing about performance and is not a CPU path of the product."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,6 @@ from test_oracle import load_case
 
 ORDER1 = [c for c in cases.ALL_CASES if "-p1-" in c]
 ORDER2 = ["ex1-d2-p2-morton-4", "ex3-d3-p2-morton-3", "gauss-d3-p2-morton"]
-GROUP_G = {2: 2, 3: 3, 4: 2}
 TOL = 1e-12  # BASELINE.json: output vectors within 1e-12 relative
 
 
@@ -35,58 +34,64 @@ def test_emulated_element_sets_match_reference(name):
     u = cases.input_vector(n)
     kw = dict(alpha=float(g["alpha"]), scale=float(g["scale"]), ip0=g["ip0"], ip1=g["ip1"])
     big = len(t.mv_lev) > 50000
-    v, sets = emu_chunks.matvec(t, u, case["max_depth"], kref=K, **kw)
+    v, sets = emu_chunks.matvec(t, u, case["max_depth"], kref=K, families=0, **kw)
     assert all(s[0] == 0 for s in sets)
     assert rel(v, g["v_dense"]) <= TOL
     if not big:
-        v, _ = emu_chunks.matvec(t, u, case["max_depth"], kref=K, dirichlet=True, order=2, **kw)
+        v, _ = emu_chunks.matvec(t, u, case["max_depth"], kref=K, dirichlet=True, order=2, families=0, **kw)
         assert rel(v, g["v_dense_diri"]) <= TOL
-        v, _ = emu_chunks.matvec(t, np.ones(n), case["max_depth"], ip0=g["ip0"], ip1=g["ip1"], order=1)
+        v, _ = emu_chunks.matvec(t, np.ones(n), case["max_depth"], ip0=g["ip0"], ip1=g["ip1"], order=1, families=0)
         assert rel(v, g["v_id"]) <= TOL
 
 
 @pytest.mark.parametrize("name", ORDER1)
-def test_emulated_group_sets_match_reference(name):
-    """sibling-group tables + group kernels: identity against the reference's golden vector, Walsh-Hadamard
-    Laplacian (+ Dirichlet) against the oracle; every fiber order must give the same vector"""
+def test_emulated_family_sets_match_reference(name):
+    """sibling-family tables + family kernel (the order-1 default): identity against the reference's golden vector,
+    Walsh-Hadamard Laplacian (+ Dirichlet) against the oracle; every fiber order must give the same vector; a general
+    dense operator on the same DA takes the per-element tables built on first use"""
     case, g, t = _tables(name)
     dim, md = case["dim"], case["max_depth"]
-    gg = GROUP_G[dim]
     n = len(g["node_lev"])
     big = len(t.mv_lev) > 50000
-    v, sets = emu_chunks.matvec(t, np.ones(n), md, ip0=g["ip0"], ip1=g["ip1"], groups=gg)
+    v, sets = emu_chunks.matvec(t, np.ones(n), md, ip0=g["ip0"], ip1=g["ip1"])
     assert rel(v, g["v_id"]) <= TOL
     # every visited element is in exactly one set
-    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
-    assert units == len(t.mv_lev)
+    assert units_of(sets, dim) == len(t.mv_lev)
     K = flat.laplace_kref(dim, 1)
     u = cases.input_vector(n)
     for diri in ((False,) if big else (False, True)):
         ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri)
         for order in ((2,) if big else (0, 1, 2)):
-            v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri,
-                                     groups=gg, order=order)
+            v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri, order=order)
             assert rel(v, ref) <= TOL
+    if not big:
+        Kd = cases.dense_operator(dim, 1)
+        v, _ = emu_chunks.matvec(t, u, md, kref=Kd, alpha=float(g["alpha"]), scale=float(g["scale"]), ip0=g["ip0"], ip1=g["ip1"])
+        assert rel(v, g["v_dense"]) <= TOL
 
 
-def test_group_sets_cover_most_of_an_adaptive_tree():
-    """on the benchmark's tree family nearly all leaves sit in complete sibling families"""
+def units_of(sets, dim):
+    return sum(s[3] * ((1 << dim) if s[0] == 2 else 1) for s in sets)
+
+
+def test_family_sets_cover_most_of_an_adaptive_tree():
+    """on the benchmark's tree family nearly all leaves sit in complete sibling families, hanging ones included"""
     import dkt
-    xyz, lev = dkt.trees.moving_ball_tree(3, 6, 10)
-    t = flat.build_tables(xyz, lev, 3, 1, 10)
-    u = cases.input_vector(len(t.node_lev))
-    v, sets = emu_chunks.matvec(t, u, 10, groups=3)
-    assert rel(v, flat.matvec(t, u)) <= TOL
-    grouped = sum(s[3] << s[2] for s in sets if s[0] == 1)
-    assert grouped >= 0.9 * len(t.mv_lev)
-    # fewer slots than one per (element, node)
-    slots_grouped = sum(s[3] * (28 if s[1] == 1 else 36) for s in sets if s[0] == 1)
-    assert slots_grouped < 0.5 * grouped * 8
+    for dim, level in ((3, 6), (4, 5)):
+        xyz, lev = dkt.trees.moving_ball_tree(dim, level, 10)
+        t = flat.build_tables(xyz, lev, dim, 1, 10)
+        u = cases.input_vector(len(t.node_lev))
+        K = flat.laplace_kref(dim, 1)
+        v, sets = emu_chunks.matvec(t, u, 10, kref=K, alpha=dim - 2.0)
+        assert rel(v, flat.matvec(t, u, Kref=K, alpha=dim - 2.0)) <= TOL
+        in_families = sum(s[3] << dim for s in sets if s[0] == 2)
+        assert in_families >= 0.9 * len(t.mv_lev)
+        assert len(t.hang_idx) > 0.2 * len(t.mv_lev)
 
 
-@pytest.mark.parametrize("name,groups", [("ball-d3-p1-morton-6", 0), ("ball-d3-p1-morton-6", 3), ("ex3-d4-p1-hilbert-3", 2),
-                                         ("gauss-d4-p1-morton", 2), ("ball-d2-p1-morton-7", 2)])
-def test_emulated_phased_sets(name, groups):
+@pytest.mark.parametrize("name,families", [("ball-d3-p1-morton-6", 0), ("ball-d3-p1-morton-6", 1), ("ex3-d4-p1-hilbert-3", 1),
+                                           ("gauss-d4-p1-morton", 1), ("ball-d2-p1-morton-7", 1), ("ball-d4-p1-morton-5", 1)])
+def test_emulated_phased_sets(name, families):
     """partitioned-DA layout ([interior | boundary] lists, three phases, visit positions with an offset):
     the phases together must give the single-pass vector"""
     case, g, t = _tables(name)
@@ -96,41 +101,16 @@ def test_emulated_phased_sets(name, groups):
     u = cases.input_vector(n)
     ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
     v, sets = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True,
-                                groups=groups, order=2, phased_seed=11)
+                                families=families, order=2, phased_seed=11)
     assert rel(v, ref) <= TOL
     assert {s[8] for s in sets} == {0, 1, 2}
-    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
-    assert units == len(t.mv_lev)
-
-
-@pytest.mark.parametrize("name,groups", [("ball-d4-p1-morton-5", "2,1"), ("ex3-d4-p1-morton-3", "3,2"), ("ex3-d4-p1-morton-3", "3,1"),
-                                         ("gauss-d4-p1-morton", "2,1"), ("ex1-d4-p1-morton-3", "1"), ("ball-d3-p1-morton-6", "3,2"),
-                                         ("ex3-d3-p1-hilbert-3", "2"), ("gauss-d3-p1-morton", "3,2")])
-def test_emulated_two_level_groups(name, groups):
-    """DKT_GROUPS=gR,gH: regular groups of 2^gR leaves, the others split into groups of 2^gH"""
-    case, g, t = _tables(name)
-    dim, md = case["dim"], case["max_depth"]
-    n = len(g["node_lev"])
-    v, sets = emu_chunks.matvec(t, np.ones(n), md, ip0=g["ip0"], ip1=g["ip1"], groups=groups)
-    assert rel(v, g["v_id"]) <= TOL
-    units = sum(s[3] * ((1 << s[2]) if s[0] == 1 else 1) for s in sets)
-    assert units == len(t.mv_lev)
-    gs = [int(x) for x in groups.split(",")]
-    assert all(s[2] in gs for s in sets if s[0] == 1)
-    if len(gs) == 2:
-        assert not any(s[0] == 1 and s[1] == 2 and s[2] == gs[0] for s in sets), "hanging groups must have the smaller size"
-    K = flat.laplace_kref(dim, 1)
-    u = cases.input_vector(n)
-    ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
-    v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True, groups=groups,
-                             order=2, phased_seed=(5 if len(t.mv_lev) < 50000 else None))
-    assert rel(v, ref) <= TOL
+    assert units_of(sets, dim) == len(t.mv_lev)
 
 
 @pytest.mark.parametrize("seed", [3, 8, 15, 21])
 def test_emulated_random_trees(seed):
     """random 2:1-balanced trees (refinement towards random spheres, some at a domain corner -> phantom elements),
-    random group spec / phase layout / fiber order: the emulated chunk path against the oracle"""
+    family / per-element tables, random phase layout / fiber order: the emulated chunk path against the oracle"""
     import dkt
     rng = np.random.default_rng(seed)
     dim = int(rng.choice([2, 3, 3, 4]))
@@ -154,7 +134,7 @@ def test_emulated_random_trees(seed):
     u = rng.uniform(-1, 1, len(t.node_lev))
     K = flat.laplace_kref(dim, 1) + 0.3 * flat.mass_kref(dim, 1)
     ref = flat.matvec(t, u, Kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True)
-    for spec in {2: ["0", "2"], 3: ["0", "3", "3,2"], 4: ["0", "2", "2,1", "3,2"]}[dim]:
-        v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True, groups=spec, order=int(rng.integers(0, 3)),
+    for spec in (0, 1):
+        v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True, families=spec, order=int(rng.integers(0, 3)),
                                  phased_seed=(None if rng.random() < 0.5 else int(rng.integers(0, 100))))
         assert rel(v, ref) <= TOL, spec

@@ -2,7 +2,7 @@
 own build_da + partition_da (dry run) + build_chunks in one process; the harness moves the ghost values with the
 library's send / receive lists around the library's (phased) chunk matvec - or (p2p=1) the library's own peer-memory flow run_matvec_dist_p2p runs stage by
 stage over all ranks, twice; the gathered result must equal the single-rank vector of the oracle.  Covers ownership, local numbering, exchange lists, the [interior | boundary] element
-order with comm/compute phases, and the sibling-group tables on real partitions - without GPUs or NCCL."""
+order with comm/compute phases, and the sibling-family tables on real partitions - without GPUs or NCCL."""
 import ctypes as C
 import os
 import subprocess
@@ -31,13 +31,13 @@ def _lib():
     return L
 
 
-@pytest.mark.parametrize("name,R,groups,overlap,p2p", [
-    ("ball-d2-p1-morton-7", 2, "0", "0", 0), ("ball-d2-p1-morton-7", 3, "2", "1", 1),
-    ("ball-d3-p1-morton-6", 3, "0", "1", 1), ("ball-d3-p1-morton-6", 8, "3", "1", 0), ("ball-d3-p1-morton-6", 2, "3,2", "0", 1),
-    ("gauss-d4-p1-morton", 4, "0", "1", 0), ("gauss-d4-p1-morton", 3, "2", "1", 1), ("ex3-d4-p1-hilbert-3", 5, "2,1", "1", 0),
-    ("ex3-d4-p1-hilbert-3", 8, "2", "0", 1), ("gauss-d3-p2-morton", 3, "0", "1", 0), ("gauss-d3-p2-morton", 4, "0", "1", 1),
+@pytest.mark.parametrize("name,R,families,overlap,p2p", [
+    ("ball-d2-p1-morton-7", 2, "0", "0", 0), ("ball-d2-p1-morton-7", 3, "1", "1", 1),
+    ("ball-d3-p1-morton-6", 3, "0", "1", 1), ("ball-d3-p1-morton-6", 8, "1", "1", 0), ("ball-d3-p1-morton-6", 2, "1", "0", 1),
+    ("gauss-d4-p1-morton", 4, "0", "1", 0), ("gauss-d4-p1-morton", 3, "1", "1", 1), ("ex3-d4-p1-hilbert-3", 5, "1", "1", 0),
+    ("ex3-d4-p1-hilbert-3", 8, "1", "0", 1), ("gauss-d3-p2-morton", 3, "0", "1", 0), ("gauss-d3-p2-morton", 4, "0", "1", 1),
 ])
-def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
+def test_emulated_partitioned_matvec(name, R, families, overlap, p2p):
     case = load_case(name)
     g = case["golden"]
     dim, order, md = case["dim"], case["order"], case["max_depth"]
@@ -57,8 +57,8 @@ def test_emulated_partitioned_matvec(name, R, groups, overlap, p2p):
     v = np.full(n, np.nan)
     info = np.zeros(8 * R, dtype=np.uint64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    old = {k: os.environ.get(k) for k in ("DKT_GROUPS", "DKT_DIST_OVERLAP")}
-    os.environ["DKT_GROUPS"] = groups
+    old = {k: os.environ.get(k) for k in ("DKT_FAMILIES", "DKT_DIST_OVERLAP")}
+    os.environ["DKT_FAMILIES"] = families
     os.environ["DKT_DIST_OVERLAP"] = overlap
     try:
         L = _lib()

@@ -13,7 +13,6 @@ from test_oracle import load_case
 
 TOL = 1e-12
 INVALID = 0xFFFFFFFF
-GROUP_SPECS = {2: ["2"], 3: ["3", "3,2"], 4: ["2", "2,1"]}
 
 
 def _sorted_rows(xyz, lev, *cols):
@@ -71,16 +70,17 @@ def test_emulated_pipeline_matches_reference(name):
             v_fast = da.matvec(u, kref=Kl, alpha=dim - 2.0)
             v_dense = da.matvec(u, kref=Kl, alpha=dim - 2.0, fastpath=False)
             assert rel(v_fast, v_dense) <= TOL
+    da_fam_v = da.matvec(u, kref=flat.laplace_kref(dim, 1), alpha=dim - 2.0, scale=0.7, dirichlet=True) if order == 1 else None
     da.close()
-    # --- the same tree with sibling-group chunk tables (opt-in DKT_GROUPS) ----------------------------------
+    # --- the same tree with per-element chunk tables only (DKT_FAMILIES=0; order 1 runs on family tables by default) ----
     if order == 1 and len(t.mv_lev) < 50000:
-        for spec in GROUP_SPECS[dim]:
-            dg = emu_full.EmuDA(case["xyz"], case["lev"], dim, order, md, sfc=sfc, ip0=g["ip0"], ip1=g["ip1"], groups=spec)
-            assert rel(dg.matvec(np.ones(n)), g["v_id"]) <= TOL
-            Kl = flat.laplace_kref(dim, 1)
-            vo = flat.matvec(t, u, Kl, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
-            assert rel(dg.matvec(u, kref=Kl, alpha=dim - 2.0, scale=0.7, dirichlet=True), vo) <= TOL
-            dg.close()
+        dg = emu_full.EmuDA(case["xyz"], case["lev"], dim, order, md, sfc=sfc, ip0=g["ip0"], ip1=g["ip1"], families=0)
+        assert rel(dg.matvec(np.ones(n)), g["v_id"]) <= TOL
+        Kl = flat.laplace_kref(dim, 1)
+        vo = flat.matvec(t, u, Kl, alpha=dim - 2.0, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=True)
+        assert rel(dg.matvec(u, kref=Kl, alpha=dim - 2.0, scale=0.7, dirichlet=True), vo) <= TOL
+        assert rel(da_fam_v, vo) <= TOL
+        dg.close()
 
 
 def test_emulated_pipeline_refuses_class_u():

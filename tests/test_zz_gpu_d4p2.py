@@ -1,6 +1,6 @@
 """GPU parity of 4-D order 2 (81 nodes per element: generic table construction + the loop-based flat kernels k_mv_big
 of dkt_matvec.cu).  The same assertions run on the CPU under the emulation (tests/test_emu_full.py); this file is
-opt-in (DKT_TEST_D4P2=1, tools/r02_groups_ab.sh) until the kernels have been confirmed on a B200."""
+opt-in (DKT_TEST_D4P2=1, tools/r02_gpu1.sh) until the kernels have been confirmed on a B200."""
 import os
 
 import numpy as np

@@ -1,7 +1,7 @@
 """The peer-memory ghost exchange (DKT_DIST_P2P, dendro-kt_b200/csrc/dkt_dist.cu: k_p2p_*) on ONE GPU: the dry-run
 DAs of all ranks of a partition live in this process, dkt_p2p_attach_local wires their exchange buffers directly, and
 the ranks' matvecs run concurrently on their own streams - same kernels, flags and protocol as between processes,
-without IPC and NCCL.  Opt-in (DKT_TEST_P2P=1, tools/r02_groups_ab.sh) until the path has been confirmed on a B200."""
+without IPC and NCCL.  Opt-in (DKT_TEST_P2P=1, tools/r02_gpu1.sh) until the path has been confirmed on a B200."""
 import os
 
 import numpy as np
@@ -14,12 +14,12 @@ TOL = 1e-12
 
 
 @pytest.mark.parametrize("nranks", [2, 3, 8])
-@pytest.mark.parametrize("groups", ["0", "2"])
-def test_p2p_exchange_in_one_process(dkt, nranks, groups):
+@pytest.mark.parametrize("families", ["0", "1"])
+def test_p2p_exchange_in_one_process(dkt, nranks, families):
     import torch
     dim, md = 4, 10
-    old = os.environ.get("DKT_GROUPS")
-    os.environ["DKT_GROUPS"] = groups
+    old = os.environ.get("DKT_FAMILIES")
+    os.environ["DKT_FAMILIES"] = families
     os.environ.pop("DKT_P2P_CHECK", None)  # it synchronises inside dkt_matvec: the ranks must be enqueued back to back here
     try:
         xyz, lev = dkt.trees.moving_ball_tree(dim, 5, md)
@@ -49,6 +49,6 @@ def test_p2p_exchange_in_one_process(dkt, nranks, groups):
             d.close()
     finally:
         if old is None:
-            os.environ.pop("DKT_GROUPS", None)
+            os.environ.pop("DKT_FAMILIES", None)
         else:
-            os.environ["DKT_GROUPS"] = old
+            os.environ["DKT_FAMILIES"] = old
