@@ -62,70 +62,16 @@
 // This file also compiles under -DDKT_EMU with tests/emu/cuda_emu.h (fibers on the CPU) - that build exists
 // ONLY so the CPU test-suite can execute the table construction and the kernels' logic against the oracle;
 // it is never part of libdkt.so.
-#include "dkt_internal.h"
+#include "dkt_chunks.h"
 
-#ifdef DKT_EMU
-#include "cuda_emu.h"
-#else
+#ifndef DKT_EMU
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
-#define DKT_LAUNCH(k, g, b, s, st) k<<<(g), (b), (s), (st)>>>
-#define DKT_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
-
-#include <algorithm>
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
 
 namespace dkt
 {
-#define CK(call)                                                                                     \
-  do                                                                                                 \
-  {                                                                                                  \
-    cudaError_t e_ = (call);                                                                         \
-    if (e_ != cudaSuccess)                                                                           \
-    {                                                                                                \
-      set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
-      return DKT_ERR_CUDA;                                                                           \
-    }                                                                                                \
-  } while (0)
 
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                       // 4096 slots per chunk
-constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;
-constexpr int MAX_LEN = 511;                         // run length of a node inside a chunk (9 bits)
-constexpr uint32_t META_LEN = 0x1FFu;
-constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty: only read by this chunk)
-constexpr uint32_t META_BDY = 0x4000u;
-constexpr uint32_t META_SHARED = 0x8000u;
-constexpr uint32_t REC_SHARED = 0x80000000u, REC_BDY = 0x40000000u, REC_GID = 0x3FFFFFFFu;  // family sets: 4-byte node records
-constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
-
-// Sibling-family sets.  The 3^dim lattice of a family lives in shared memory at  Ls[f * S + p0 + 3 p1 + SA p2 + SB p3];
-// one thread (a "quad") handles the 4 children that differ in dimensions 0 and 1, the 2^(dim-2) quads of a family are
-// neighbouring lanes.  S, SA, SB make every 8-byte access of the quad phase conflict-free (searched, half-warp model:
-// tools/smem_sim.py validated that model against ncu in round 1).
-template <int DIM>
-struct Fam
-{
-  static constexpr int NL = DIM - 2;                 // dimensions spread over lanes
-  static constexpr int QPF = 1 << NL;                // quads (threads) per family
-  static constexpr int FPW = 32 / QPF;               // families per warp
-  static constexpr int L = (DIM == 2 ? 9 : DIM == 3 ? 27 : 81);
-  static constexpr int SA = (DIM == 4 ? 10 : 12), SB = 36;
-  static constexpr int S = (DIM == 2 ? 9 : DIM == 3 ? 33 : 101);
-  static constexpr int N = 1 << DIM;
-  static constexpr int NS = 1 << NL;                 // (s2, s3) combinations: lattice points of a quad = 9 * NS
-  static constexpr int TPB = 128;
-  static constexpr int UPC = TPB / QPF;              // families per chunk (32 / 64 / 128: 512 elements)
-};
-__host__ __device__ constexpr int fam_L(int dim) { return dim == 2 ? 9 : dim == 3 ? 27 : 81; }
-__host__ __device__ constexpr int fam_S(int dim) { return dim == 2 ? 9 : dim == 3 ? 33 : 101; }
-__host__ __device__ constexpr int fam_SA(int dim) { return dim == 4 ? 10 : 12; }
-__host__ __device__ constexpr int fam_UPC(int dim) { return 128 >> (dim - 2); }
-// natural lattice index k = p0 + 3 p1 + 9 p2 + 27 p3  ->  offset inside the family's shared-memory lattice
-__host__ __device__ constexpr int fam_laddr(int dim, int k) { return (k % 9) + fam_SA(dim) * ((k / 9) % 3) + 36 * (k / 27); }
 
 // Rows (of N slots) per chunk: bounded by the block sort capacity and by ONE element per thread
 // in the matvec kernels.
@@ -137,9 +83,6 @@ __host__ __device__ constexpr int fam_laddr(int dim, int k) { return (k % 9) + f
 #endif
 #ifndef DKT_HANG_MINB
 #define DKT_HANG_MINB 4
-#endif
-#ifndef DKT_FAM_MINB
-#define DKT_FAM_MINB 3   // resident CTAs per SM the family kernel is compiled for
 #endif
 int rows_per_chunk(int N)
 {
@@ -840,6 +783,35 @@ static int add_elem_set(DA &da, std::vector<ChunkSet> &sets, std::vector<Pending
   return DKT_OK;
 }
 
+// Inside a chunk the order of the families is free: the ones without hanging points go first, so that whole warps of the
+// kernel (FPW families each) skip the hanging-node code.  src[u] = unit that moves to position u.
+__global__ void k_family_order(const uint32_t *frec, uint64_t n, int upc, uint32_t *src)
+{
+  const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t u0 = c * (uint64_t)upc;
+  if (u0 >= n) return;
+  const int nu = (int)min((uint64_t)upc, n - u0);
+  int k = 0;
+  for (int pass = 0; pass < 2; pass++)
+    for (int i = 0; i < nu; i++)
+    {
+      const uint32_t *fr = frec + (u0 + i) * 4;
+      const int hang = (fr[0] | fr[1] | fr[2]) != 0u;
+      if (hang == pass) src[u0 + k++] = (uint32_t)(u0 + i);
+    }
+}
+__global__ void k_family_permute(const uint32_t *src, uint64_t n, int L, const uint32_t *Uin, const uint32_t *frecIn, uint32_t *Uout,
+                                 uint32_t *frecOut)
+{
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n * L) return;
+  const uint64_t u = i / L;
+  const int k = (int)(i % L);
+  const uint64_t s = src[u];
+  Uout[i] = Uin[s * L + k];
+  if (k < 4) frecOut[u * 4 + k] = frecIn[s * 4 + k];
+}
+
 // family set: units [a, b) of the gathered unit slot table / records of one class
 static int add_family_set(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingSet> &pend, const uint32_t *U, const uint32_t *frec, uint64_t n,
                           int phase)
@@ -851,13 +823,17 @@ static int add_family_set(DA &da, std::vector<ChunkSet> &sets, std::vector<Pendi
   cs.spu = fam_L(da.dim);
   cs.elemsPerChunk = fam_UPC(da.dim);
   const uint32_t nChunks = (uint32_t)((n + cs.elemsPerChunk - 1) / cs.elemsPerChunk);
-  uint32_t *Uc = nullptr;
+  uint32_t *Uc = nullptr, *src = nullptr;
   CK(cudaMalloc((void **)&Uc, n * cs.spu * sizeof(uint32_t)));
-  CK(cudaMemcpyAsync(Uc, U, n * cs.spu * sizeof(uint32_t), cudaMemcpyDeviceToDevice, da.stream));
+  CK(cudaMalloc((void **)&src, n * sizeof(uint32_t)));
   // records padded to whole chunks: the kernel copies them chunk by chunk
   CK(cudaMalloc((void **)&cs.d_frec, (size_t)nChunks * cs.elemsPerChunk * 4 * sizeof(uint32_t)));
   CK(cudaMemsetAsync(cs.d_frec, 0, (size_t)nChunks * cs.elemsPerChunk * 4 * sizeof(uint32_t), da.stream));
-  CK(cudaMemcpyAsync(cs.d_frec, frec, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, da.stream));
+  DKT_LAUNCH(k_family_order, nblk(nChunks), 256, 0, da.stream)(frec, n, (int)cs.elemsPerChunk, src);
+  DKT_LAUNCH(k_family_permute, nblk(n * cs.spu), 256, 0, da.stream)(src, n, cs.spu, U, frec, Uc, cs.d_frec);
+  g_launches += 2;
+  CK(cudaStreamSynchronize(da.stream));
+  cudaFree(src);
   pend.push_back({sets.size() - 1, Uc});
   return DKT_OK;
 }
@@ -1177,29 +1153,6 @@ __device__ __forceinline__ void tensor_interp3(const double (&ip)[2][M * M], int
 }
 
 
-// internal operator kind: K = (1/N) H diag(d) H with H the N x N Walsh-Hadamard matrix (N = 2^dim,
-// order 1).  Every operator whose 1-D factors are 2x2 matrices of the form [[a,b],[b,a]] - mass,
-// Laplacian and their combinations on axis-aligned cells - has this form; run_typed3 detects it
-// from the dense kref on the host.  2*dim*N/2 add/sub pairs + N multiplies instead of N^2 FMAs.
-constexpr int OP_HADAMARD = 100;
-
-template <int N>
-__device__ __forceinline__ void wht(double *v)
-{
-#pragma unroll
-  for (int s = 1; s < N; s <<= 1)
-  {
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      if (i & s) continue;
-      const double a = v[i], b = v[i + s];
-      v[i] = a + b;
-      v[i + s] = a - b;
-    }
-  }
-}
-
 // Exact order-1 parent->child interpolation in XOR-permuted coordinates: every axis uses
 // A0 = [[1, 1/2], [0, 1/2]] (input k -> output j), i.e. child'[s] = 2^-|s| * sum_{t subset of s} parent'[t]
 // (a subset-sum transform), and its transpose parent'[t] += sum_{s superset of t} 2^-|s| child'[s].
@@ -1265,26 +1218,6 @@ __device__ __forceinline__ void apply_op3(const Mv3Params<DIM, ORDER> &p, int le
     }
   }
 }
-
-#ifndef DKT_EMU
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
-{
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
-{
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-#else
-inline void cp_async8(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 8); }
-inline void cp_async4(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 4); }
-inline void cp_async_commit() {}
-inline void cp_async_wait_all() {}
-#endif
 
 // undo the XOR slot schedule in registers: v[r] <- v[r ^ c]
 template <int DIM, int N, typename T>
@@ -1549,362 +1482,6 @@ static int launch_one(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p)
   g_launches++;
   return DKT_OK;
 }
-// ------------------------------------------------------------------------------------------
-// sibling-family kernel (order 1, identity / Walsh-Hadamard operators, exact interpolation)
-// ------------------------------------------------------------------------------------------
-// One CTA per chunk of UPC families (512 elements), 128 threads, no loop over chunks: 3-4 CTAs share an SM and
-// overlap each other's memory and compute phases.
-//   L0  thread 0: cp.async.bulk (TMA 1-D bulk copies, mbarrier completion) of the chunk's contiguous tables - node
-//       records, rk16, inv16, family records, jd|cnt - into shared memory
-//   L1  all threads, once the records are there: cp.async 8-byte gathers un[n] <- u[gid[n]]           -- barrier A
-//   F   warp-local (a warp owns FPW families in every phase up to Q): thread per lattice slot,
-//       Ls[f][p] = lscale(level f) * un[rk16[slot]]; a hanging point takes the mean of the corners of G(p) instead
-//       (exact order-1 interpolation from the parent's nodes = the family's corners)                  -- __syncwarp
-//   Q   thread per QUAD (the 4 children differing in dimensions 0, 1; the quads of a family are neighbouring lanes):
-//       per child 2^dim conflict-free LDS with static offsets, the elemental operator (identity or Walsh-Hadamard
-//       form; dimensions >= 2 are addressed XOR-permuted, with which both commute), Q1's scalar tau_c off its corner,
-//       accumulation into the quad's 9 * 2^(dim-2) lattice points in registers; the points shared with the other
-//       quads are summed with 1-2 shuffles each; in a family with hanging points the transposed interpolation then
-//       runs on the registers, one dimension at a time (each lane owns the corner side of its XOR-permuted
-//       dimensions, so no further communication); __syncwarp; the sums go back to Ls in place      -- barrier B
-//   N   thread per chunk node: acc = sum_k Ls[inv16[jd[k] + n]], one plain store (node private to the chunk)
-//       or one fp64 RED
-struct MvfParams
-{
-  const double *in;
-  double *out;
-  const uint16_t *rk16, *inv16, *jd;
-  const uint32_t *frec, *rec, *nloc;
-  const uint64_t *node_off;
-  uint32_t nSet, nChunks, jdStride, ncap;  // ncap: multiple of 4, >= the largest chunk's padded node count
-  double lscale[32];
-  double K[16];  // Walsh-Hadamard form: diagonal / N
-};
-
-#ifndef DKT_EMU
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  while (!done)
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done)
-                 : "r"(a), "r"(parity)
-                 : "memory");
-}
-#else
-// emulation: the barrier word counts [expected bytes + 1 | completed bytes]; a waiting fiber lets the others run
-inline void mbar_init(uint64_t *bar, int) { *bar = 0; }
-inline void mbar_init_fence() {}
-inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += (uint64_t)bytes + 1; }
-inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  memcpy(dst, src, bytes);
-  *bar += (uint64_t)bytes << 32;
-}
-inline void mbar_wait(uint64_t *bar, uint32_t)
-{
-  while ((uint32_t)*bar == 0 || (*bar >> 32) + 1 < (uint32_t)*bar) emu::spin_yield();
-}
-#endif
-
-// shared-memory layout of k_mvf (bytes; every section a multiple of 16)
-template <int DIM>
-struct FamSmem
-{
-  using F = Fam<DIM>;
-  uint32_t oUn, oRec, oRk, oInv, oFrec, oJd, oBar, total;
-  __host__ __device__ FamSmem(uint32_t ncap, uint32_t jdStride)
-  {
-    uint32_t o = F::UPC * F::S * 8;
-    oUn = o; o += (ncap + 2) * 8;
-    oRec = o; o += ncap * 4;
-    oRk = o; o += F::UPC * F::L * 2;
-    oInv = o; o += F::UPC * F::L * 2;
-    oFrec = o; o += F::UPC * 16;
-    oJd = o; o += 2 * jdStride * 2;
-    oBar = o; o += 16;
-    total = o;
-  }
-};
-
-template <int DIM, int OPKIND, bool DIRI>
-__global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __grid_constant__ MvfParams p)
-{
-  using F = Fam<DIM>;
-  constexpr int L = F::L, S = F::S, SA = F::SA, SB = F::SB, N = F::N, NS = F::NS, NL = F::NL, QPF = F::QPF, FPW = F::FPW, UPC = F::UPC,
-                TPB = F::TPB;
-  static_assert((UPC * S * 8) % 16 == 0 && (UPC * L * 2) % 16 == 0, "bulk copies need 16-byte sections");
-  DKT_DYN_SMEM(double, sm);
-  const FamSmem<DIM> lay(p.ncap, p.jdStride);
-  char *smc = (char *)sm;
-  double *Ls = sm;
-  double *un = (double *)(smc + lay.oUn);
-  uint32_t *rec = (uint32_t *)(smc + lay.oRec);
-  uint16_t *rk = (uint16_t *)(smc + lay.oRk);
-  uint16_t *inv = (uint16_t *)(smc + lay.oInv);
-  uint32_t *frec = (uint32_t *)(smc + lay.oFrec);
-  uint16_t *jd = (uint16_t *)(smc + lay.oJd);
-  uint64_t *bar = (uint64_t *)(smc + lay.oBar);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t c = blockIdx.x;
-  const uint32_t u0 = c * UPC;
-  const int nfam = (int)min((uint32_t)UPC, p.nSet - u0);
-  const uint64_t noff = p.node_off[c];
-  const int nloc = (int)p.nloc[c];
-  const uint32_t recBytes = (uint32_t)((nloc + 3) & ~3) * 4u;
-
-  // ---- L0: bulk copies of the chunk's tables
-  if (tid == 0)
-  {
-    mbar_init(bar, 1);
-    mbar_init(bar + 1, 1);
-    mbar_init_fence();
-  }
-  __syncthreads();
-  if (tid == 0)
-  {
-    mbar_expect_tx(bar, recBytes);
-    bulk_g2s(rec, p.rec + noff, recBytes, bar);
-    const uint32_t slotBytes = UPC * L * 2, frecBytes = UPC * 16, jdBytes = 2 * p.jdStride * 2;
-    mbar_expect_tx(bar + 1, 2 * slotBytes + frecBytes + jdBytes);
-    bulk_g2s(rk, p.rk16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
-    bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
-    bulk_g2s(frec, p.frec + (uint64_t)c * (UPC * 4), frecBytes, bar + 1);
-    bulk_g2s(jd, p.jd + (uint64_t)c * (2 * p.jdStride), jdBytes, bar + 1);
-  }
-  // ---- L1: gather the chunk's node values
-  mbar_wait(bar, 0);
-  for (int n = tid; n < nloc; n += TPB)
-  {
-    const uint32_t r = rec[n];
-    if (DIRI && (r & REC_BDY)) un[n] = 0.0;
-    else cp_async8(un + n, p.in + (r & REC_GID));
-  }
-  if (tid == 0) un[nloc] = 0.0;  // what the slots without a node read
-  cp_async_commit();
-  mbar_wait(bar + 1, 0);
-  cp_async_wait_all();
-  __syncthreads();  // A
-
-  const int fw0 = warp * FPW;
-  const int nfw = min(FPW, nfam - fw0);  // families of this warp
-  if (nfw > 0)
-  {
-    // ---- F: fill the lattices of the warp's families
-    for (int i = lane; i < nfw * L; i += 32)
-    {
-      const int fl = i / L, k = i - fl * L, f = fw0 + fl;
-      const uint16_t *rkf = rk + f * L;
-      const uint32_t *fr = frec + f * 4;
-      double v;
-      if (!((fr[k / 27] >> (k % 27)) & 1u)) v = un[rkf[k]];
-      else
-      {
-        // a hanging point: mean of the corners of the smallest face of the parent cell that contains it
-        int st[DIM];
-        int m = 0;
-        for (int d = 0, kk = k, p3 = 1; d < DIM; d++, kk /= 3, p3 *= 3)
-          if (kk % 3 == 1) st[m++] = p3;
-        v = 0.0;
-        for (int sub = 0; sub < (1 << m); sub++)
-        {
-          int kc = k;
-          for (int j = 0; j < m; j++) kc += ((sub >> j) & 1) ? st[j] : -st[j];
-          v += un[rkf[kc]];
-        }
-        v *= 1.0 / (double)(1 << m);
-      }
-      if (OPKIND != DKT_OP_IDENTITY) v *= p.lscale[fr[3] & 31u];
-      Ls[f * S + fam_laddr(DIM, k)] = v;
-    }
-    __syncwarp();
-
-    // ---- Q: one quad per thread
-    const int fl = lane / QPF, j = lane % QPF;
-    const bool act = fl < nfw;
-    const int f = fw0 + (act ? fl : 0);
-    const int c2 = j & 1, c3 = (j >> 1) & 1;
-    double *Lf = Ls + f * S;
-    const uint32_t *fr = frec + f * 4;
-    int boff[NS];        // where the quad's points with (s2, s3) start; s_d = 0: the corner side 2 c_d, s_d = 1: the middle
-    uint32_t g[NS];      // their hanging bits (bit i0 + 3 i1)
-#pragma unroll
-    for (int sg = 0; sg < NS; sg++)
-    {
-      const int s2 = sg & 1, s3 = sg >> 1;
-      const int p2 = NL >= 1 ? (s2 ? 1 : 2 * c2) : 0, p3 = NL >= 2 ? (s3 ? 1 : 2 * c3) : 0;
-      boff[sg] = SA * p2 + SB * p3;
-      g[sg] = (fr[DIM == 4 ? p3 : 0] >> (9 * p2)) & 0x1FFu;
-    }
-    const bool hangfam = act && (fr[0] | fr[1] | fr[2]) != 0u;
-    double acc[9 * NS];
-#pragma unroll
-    for (int cq = 0; cq < 4; cq++)
-    {
-      const int c0 = cq & 1, c1 = cq >> 1;
-      double e[N];
-#pragma unroll
-      for (int r = 0; r < N; r++) e[r] = Lf[boff[r >> 2] + (c0 + (r & 1)) + 3 * (c1 + ((r >> 1) & 1))];
-      if (OPKIND == OP_HADAMARD)
-      {
-        wht<N>(e);
-#pragma unroll
-        for (int i = 0; i < N; i++) e[i] *= p.K[i];
-        wht<N>(e);
-      }
-      if (hangfam)
-      {
-        // quirk Q1 on a family (see k_family_check): tau = sum over the child's hanging ranks of 2^-|odd| eout, off its corner
-        double tau = 0.0;
-#pragma unroll
-        for (int r = 0; r < N; r++)
-        {
-          const int i0 = c0 + (r & 1), i1 = c1 + ((r >> 1) & 1), sg = r >> 2;
-          const int nodd = (i0 == 1) + (i1 == 1) + (sg & 1) + (sg >> 1);
-          if (nodd == 0) continue;  // the corner itself
-          const double w = 1.0 / (double)(1 << nodd);
-          if ((g[sg] >> (i0 + 3 * i1)) & 1u) tau = fma(w, e[r], tau);
-        }
-        e[c0 | (c1 << 1)] -= tau;
-      }
-#pragma unroll
-      for (int r = 0; r < N; r++)
-      {
-        const int r0 = r & 1, r1 = (r >> 1) & 1;
-        const int a = (c0 + r0) + 3 * (c1 + r1) + 9 * (r >> 2);
-        if ((c0 == 0 || r0 == 1) && (c1 == 0 || r1 == 1)) acc[a] = e[r];  // first child that touches the point
-        else acc[a] += e[r];
-      }
-    }
-    // the middle points of the lane dimensions are shared with the neighbouring quads
-#pragma unroll
-    for (int sg = 1; sg < NS; sg++)
-#pragma unroll
-      for (int i = 0; i < 9; i++)
-      {
-        double v = acc[i + 9 * sg];
-        if (sg & 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if (sg & 2) v += __shfl_xor_sync(0xffffffffu, v, 2);
-        acc[i + 9 * sg] = v;
-      }
-    if (hangfam)
-    {
-      // transposed interpolation of the hanging points towards the corners, one dimension at a time
-#pragma unroll
-      for (int sg = 0; sg < NS; sg++)
-#pragma unroll
-        for (int i1 = 0; i1 < 3; i1++)
-          if ((g[sg] >> (1 + 3 * i1)) & 1u)
-          {
-            const double h = 0.5 * acc[1 + 3 * i1 + 9 * sg];
-            acc[0 + 3 * i1 + 9 * sg] += h;
-            acc[2 + 3 * i1 + 9 * sg] += h;
-          }
-#pragma unroll
-      for (int sg = 0; sg < NS; sg++)
-#pragma unroll
-        for (int i0 = 0; i0 < 3; i0++)
-          if ((g[sg] >> (i0 + 3)) & 1u)
-          {
-            const double h = 0.5 * acc[i0 + 3 + 9 * sg];
-            acc[i0 + 9 * sg] += h;
-            acc[i0 + 6 + 9 * sg] += h;
-          }
-#pragma unroll
-      for (int d = 0; d < NL; d++)
-#pragma unroll
-        for (int sg = 0; sg < NS; sg++)
-        {
-          if (!((sg >> d) & 1)) continue;
-#pragma unroll
-          for (int i = 0; i < 9; i++)
-            if ((g[sg] >> i) & 1u) acc[i + 9 * (sg ^ (1 << d))] += 0.5 * acc[i + 9 * sg];
-        }
-    }
-    __syncwarp();  // every lane of the warp has read its lattice points
-    if (act)
-    {
-#pragma unroll
-      for (int sg = 0; sg < NS; sg++)
-      {
-        // a shared point is stored by the quad with c_d == 0
-        if (((sg & 1) && c2) || ((sg & 2) && c3)) continue;
-#pragma unroll
-        for (int i = 0; i < 9; i++) Lf[boff[sg] + i] = acc[i + 9 * sg];
-      }
-    }
-  }
-  __syncthreads();  // B
-
-  // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
-  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.
-  {
-    const uint16_t *cnt = jd + p.jdStride;
-    const int cnt0 = cnt[0];
-    for (int n = tid; n < cnt0; n += TPB)
-    {
-      double a = Ls[inv[n]];  // jd[0] == 0
-      for (int k = 1; n < (int)cnt[k]; k++) a += Ls[inv[(int)jd[k] + n]];
-      const uint32_t r = rec[n];
-      if (DIRI && (r & REC_BDY)) continue;
-      if (r & REC_SHARED) atomicAdd(p.out + (r & REC_GID), a);
-      else p.out[r & REC_GID] = a;
-    }
-  }
-}
-
-template <int DIM, int OPKIND, bool DIRI>
-static int launch_family_one(DA &da, const ChunkSet &cs, MvfParams &p)
-{
-  using F = Fam<DIM>;
-  if (cs.spu != F::L || (int)cs.elemsPerChunk != F::UPC) { set_error("internal: family set does not match its kernel"); return DKT_ERR_INVALID; }
-  p.rk16 = cs.d_rk16; p.inv16 = cs.d_inv16; p.jd = cs.d_jd; p.frec = cs.d_frec; p.rec = (const uint32_t *)cs.d_rec; p.nloc = cs.d_nloc;
-  p.node_off = cs.d_node_off;
-  p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.jdStride = cs.jdStride;
-  p.ncap = (cs.maxNloc + 3) & ~3u;
-  const FamSmem<DIM> lay(p.ncap, p.jdStride);
-  auto kern = k_mvf<DIM, OPKIND, DIRI>;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-  DKT_LAUNCH(kern, cs.nChunks, F::TPB, lay.total, da.cur ? da.cur : da.stream)(p);
-  g_launches++;
-  return DKT_OK;
-}
-
-template <int DIM, int ORDER, int OPKIND, bool DIRI>
-static int launch_family(DA &da, const ChunkSet &cs, Mv3Params<DIM, ORDER> &p3)
-{
-  if constexpr (ORDER == 1 && (OPKIND == DKT_OP_IDENTITY || OPKIND == OP_HADAMARD))
-  {
-    static thread_local MvfParams p;
-    p.in = p3.in;
-    p.out = p3.out;
-    for (int l = 0; l < 32; l++) p.lscale[l] = p3.lscale[l];
-    for (int i = 0; i < 16; i++) p.K[i] = i < (1 << DIM) ? p3.K[i] : 0.0;
-    return launch_family_one<DIM, OPKIND, DIRI>(da, cs, p);
-  }
-  set_error("internal: no sibling-family kernel for this (order, operator)");
-  return DKT_ERR_UNSUPPORTED;
-}
-
 template <int DIM, int ORDER, int OPKIND, bool DIRI>
 static int launch_mv3(DA &da, const std::vector<ChunkSet> &sets, Mv3Params<DIM, ORDER> &p, unsigned phaseMask)
 {
@@ -1937,7 +1514,16 @@ static int launch_mv3(DA &da, const std::vector<ChunkSet> &sets, Mv3Params<DIM, 
       }
       k++;
     }
-    if (cs.kind == 2) rc = launch_family<DIM, ORDER, OPKIND, DIRI>(da, cs, p);
+    if (cs.kind == 2)
+    {
+      if constexpr (ORDER == 1 && (OPKIND == DKT_OP_IDENTITY || OPKIND == OP_HADAMARD))
+        rc = launch_family_set(da, cs, OPKIND, DIRI, p.in, p.out, p.lscale, p.K);
+      else
+      {
+        set_error("internal: no sibling-family kernel for this (order, operator)");
+        rc = DKT_ERR_UNSUPPORTED;
+      }
+    }
     else if (cs.rows == 1)
     {
       if (cs.maxNloc <= 6u * TPB_R) rc = launch_one<DIM, ORDER, OPKIND, DIRI, false, TPB_R, 6, false>(da, cs, p);

@@ -1,0 +1,459 @@
+// Sibling-family matvec kernel (order 1, identity / Walsh-Hadamard operators, exact interpolation).
+//
+// One UNIT is a complete family - the 2^dim leaves of one parent - with its 3^dim node lattice (tables: dkt_chunks.cu,
+// k_family_units / k_family_check / k_chunk_build).  One CTA per chunk of UPC families (512 elements), 128 threads, no loop
+// over chunks: 3-4 CTAs share an SM and overlap each other's memory and compute phases.
+//   L0  thread 0: cp.async.bulk (TMA 1-D bulk copies, mbarrier completion; SASS UBLKCP) of the chunk's contiguous tables -
+//       node records, rk16, inv16, family records, jd|cnt - into shared memory
+//   L1  all threads, once the records are there: cp.async 8-byte gathers un[n] <- u[gid[n]]               -- barrier A
+//   Everything up to barrier B is warp-local: a warp owns FPW families, one thread per QUAD (the 4 children that differ in
+//   dimensions 0, 1; the 2^(dim-2) quads of a family are neighbouring lanes).
+//   F   the quads of a family share out its lattice points (static addressing, no index arithmetic):
+//       Ls[f][p] = lscale(level f) * un[rk16[slot]]; then (__syncwarp) a hanging point takes the mean of the corners of
+//       G(p) (exact order-1 interpolation from the parent's nodes = the family's corners)                 -- __syncwarp
+//   Q   per child 2^dim conflict-free LDS with static offsets, the elemental operator (identity or Walsh-Hadamard form;
+//       dimensions >= 2 are addressed XOR-permuted, with which both commute), Q1's scalar tau_c off its corner
+//       (k_family_check), accumulation into the quad's 9 * 2^(dim-2) lattice points in registers; the points shared with
+//       the other quads are summed with 1-2 shuffles each; in a family with hanging points the transposed interpolation
+//       then runs on the registers, one dimension at a time (each lane owns the corner side of its XOR-permuted
+//       dimensions, so no further communication); __syncwarp; the sums go back to Ls in place           -- barrier B
+//   N   thread per chunk node: acc = sum_k Ls[inv16[jd[k] + n]], one plain store (node private to the chunk)
+//       or one fp64 RED
+// Also compiles under -DDKT_EMU (tests/emu): CPU test infrastructure only.
+#include "dkt_chunks.h"
+
+namespace dkt
+{
+#ifndef DKT_FAM_MINB
+#define DKT_FAM_MINB 3   // resident CTAs per SM the family kernel is compiled for
+#endif
+
+struct MvfParams
+{
+  const double *in;
+  double *out;
+  const uint16_t *rk16, *inv16, *jd;
+  const uint32_t *frec, *rec, *nloc;
+  const uint64_t *node_off;
+  uint32_t nSet, nChunks, jdStride, ncap;  // ncap: multiple of 4, >= the largest chunk's padded node count
+  double lscale[32];
+  double K[16];  // Walsh-Hadamard form: diagonal / N
+};
+
+#ifndef DKT_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+}
+#else
+// emulation: the barrier word counts [expected bytes + 1 | completed bytes]; a waiting fiber lets the others run
+inline void mbar_init(uint64_t *bar, int) { *bar = 0; }
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += (uint64_t)bytes + 1; }
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  memcpy(dst, src, bytes);
+  *bar += (uint64_t)bytes << 32;
+}
+inline void mbar_wait(uint64_t *bar, uint32_t)
+{
+  while ((uint32_t)*bar == 0 || (*bar >> 32) + 1 < (uint32_t)*bar) emu::spin_yield();
+}
+#endif
+
+// acc += a (acc = fma(a, w, acc)) under a predicate.  nvcc turns `if (p) acc += a` into an unconditional add and two FSELs;
+// the PTX predicate keeps it ONE predicated instruction.
+#ifndef DKT_EMU
+__device__ __forceinline__ void add_if(double &acc, double a, uint32_t p)
+{
+  asm("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q add.rn.f64 %0, %0, %1;\n}\n" : "+d"(acc) : "d"(a), "r"(p));
+}
+__device__ __forceinline__ void fma_if(double &acc, double a, double w, uint32_t p)
+{
+  asm("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q fma.rn.f64 %0, %1, %2, %0;\n}\n" : "+d"(acc) : "d"(a), "d"(w), "r"(p));
+}
+#else
+inline void add_if(double &acc, double a, uint32_t p) { if (p) acc += a; }
+inline void fma_if(double &acc, double a, double w, uint32_t p) { if (p) acc = fma(a, w, acc); }
+#endif
+
+// shared-memory layout of k_mvf (bytes; every section a multiple of 16)
+template <int DIM>
+struct FamSmem
+{
+  using F = Fam<DIM>;
+  uint32_t oUn, oRec, oRk, oInv, oFrec, oJd, oBar, total;
+  __host__ __device__ FamSmem(uint32_t ncap, uint32_t jdStride)
+  {
+    uint32_t o = F::UPC * F::S * 8;
+    oUn = o; o += (ncap + 2) * 8;
+    oRec = o; o += ncap * 4;
+    oRk = o; o += F::UPC * F::L * 2;
+    oInv = o; o += F::UPC * F::L * 2;
+    oFrec = o; o += F::UPC * 16;
+    oJd = o; o += 2 * jdStride * 2;
+    oBar = o; o += 16;
+    total = o;
+  }
+};
+
+template <int DIM, int OPKIND, bool DIRI>
+__global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __grid_constant__ MvfParams p)
+{
+  using F = Fam<DIM>;
+  constexpr int L = F::L, S = F::S, SA = F::SA, SB = F::SB, N = F::N, NS = F::NS, NL = F::NL, QPF = F::QPF, FPW = F::FPW, UPC = F::UPC,
+                TPB = F::TPB;
+  static_assert((UPC * S * 8) % 16 == 0 && (UPC * L * 2) % 16 == 0, "bulk copies need 16-byte sections");
+  DKT_DYN_SMEM(double, sm);
+  const FamSmem<DIM> lay(p.ncap, p.jdStride);
+  char *smc = (char *)sm;
+  double *Ls = sm;
+  double *un = (double *)(smc + lay.oUn);
+  uint32_t *rec = (uint32_t *)(smc + lay.oRec);
+  uint16_t *rk = (uint16_t *)(smc + lay.oRk);
+  uint16_t *inv = (uint16_t *)(smc + lay.oInv);
+  uint32_t *frec = (uint32_t *)(smc + lay.oFrec);
+  uint16_t *jd = (uint16_t *)(smc + lay.oJd);
+  uint64_t *bar = (uint64_t *)(smc + lay.oBar);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t c = blockIdx.x;
+  const uint32_t u0 = c * UPC;
+  const int nfam = (int)min((uint32_t)UPC, p.nSet - u0);
+  const uint64_t noff = p.node_off[c];
+  const int nloc = (int)p.nloc[c];
+  const uint32_t recBytes = (uint32_t)((nloc + 3) & ~3) * 4u;
+
+  // ---- L0: bulk copies of the chunk's tables
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+    mbar_expect_tx(bar, recBytes);
+    bulk_g2s(rec, p.rec + noff, recBytes, bar);
+    const uint32_t slotBytes = UPC * L * 2, frecBytes = UPC * 16, jdBytes = 2 * p.jdStride * 2;
+    mbar_expect_tx(bar + 1, 2 * slotBytes + frecBytes + jdBytes);
+    bulk_g2s(rk, p.rk16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
+    bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
+    bulk_g2s(frec, p.frec + (uint64_t)c * (UPC * 4), frecBytes, bar + 1);
+    bulk_g2s(jd, p.jd + (uint64_t)c * (2 * p.jdStride), jdBytes, bar + 1);
+  }
+  // ---- L1: gather the chunk's node values
+  mbar_wait(bar, 0);
+  for (int n = tid; n < nloc; n += TPB)
+  {
+    const uint32_t r = rec[n];
+    if (DIRI && (r & REC_BDY)) un[n] = 0.0;
+    else cp_async8(un + n, p.in + (r & REC_GID));
+  }
+  if (tid == 0) un[nloc] = 0.0;  // what the slots without a node read
+  cp_async_commit();
+  mbar_wait(bar + 1, 0);
+  cp_async_wait_all();
+  __syncthreads();  // A
+
+  const int fw0 = warp * FPW;
+  const int nfw = min(FPW, nfam - fw0);  // families of this warp
+  if (nfw > 0)
+  {
+    const int fl = lane / QPF, j = lane % QPF;
+    const bool act = fl < nfw;
+    const int f = fw0 + (act ? fl : 0);
+    const int c2 = j & 1, c3 = (j >> 1) & 1;
+    double *Lf = Ls + f * S;
+    const uint16_t *rkf = rk + f * L;
+    const uint32_t *fr = frec + f * 4;
+    // the quad's lattice points: 9 (i0, i1) x (s2, s3); s_d = 0: the corner side p_d = 2 c_d, s_d = 1: the middle p_d = 1
+    int boff[NS];        // shared-memory offset of the points with (s2, s3)
+    int kb[NS];          // their natural lattice index 9 p2 + 27 p3 (index into rk16)
+    uint32_t g[NS];      // their hanging bits (bit i0 + 3 i1)
+#pragma unroll
+    for (int sg = 0; sg < NS; sg++)
+    {
+      const int s2 = sg & 1, s3 = sg >> 1;
+      const int p2 = NL >= 1 ? (s2 ? 1 : 2 * c2) : 0, p3 = NL >= 2 ? (s3 ? 1 : 2 * c3) : 0;
+      boff[sg] = SA * p2 + SB * p3;
+      kb[sg] = 9 * p2 + 27 * p3;
+      g[sg] = (fr[DIM == 4 ? p3 : 0] >> (9 * p2)) & 0x1FFu;
+    }
+    const bool hangfam = act && (fr[0] | fr[1] | fr[2]) != 0u;
+
+    // ---- F: fill the family's lattice.  A point with (s2, s3) is shared by the 2^|s| quads that differ in those dimensions;
+    // they take its 9 (i0, i1) in turn (static, predicated code: no index arithmetic).
+    {
+      const double sc = OPKIND != DKT_OP_IDENTITY ? p.lscale[fr[3] & 31u] : 1.0;
+      if (act)
+      {
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
+        {
+          const int nsh = (sg == 0 ? 1 : sg == 3 ? 4 : 2);
+          const int me = (sg == 0 ? 0 : sg == 1 ? c2 : sg == 2 ? c3 : j);
+#pragma unroll
+          for (int i = 0; i < 9; i++)
+            if (nsh == 1 || (i % nsh) == me) Lf[boff[sg] + i] = un[rkf[kb[sg] + i]] * sc;  // a hanging point reads the zero entry
+        }
+      }
+      __syncwarp();
+      // Hanging points: exact order-1 interpolation from the corners of G(p), one dimension at a time - the points whose LOWEST
+      // odd coordinate is d take the mean of their two neighbours along d (corners, or hanging points of an earlier pass;
+      // k_family_check's (C1) guarantees those hang too).  Quads that share a point compute the same value.
+      if (NL >= 2)
+      {
+        if (hangfam)
+        {
+#pragma unroll
+          for (int i1 = 0; i1 < 3; i1 += 2)
+#pragma unroll
+            for (int i0 = 0; i0 < 3; i0 += 2)
+              if ((g[2] >> (i0 + 3 * i1)) & 1u)
+              {
+                const int o = i0 + 3 * i1 + SA * 2 * c2;
+                Lf[boff[2] + i0 + 3 * i1] = 0.5 * (Lf[o] + Lf[o + 2 * SB]);
+              }
+        }
+        __syncwarp();
+      }
+      if (NL >= 1)
+      {
+        if (hangfam)
+        {
+#pragma unroll
+          for (int s3 = 0; s3 < (NL >= 2 ? 2 : 1); s3++)
+#pragma unroll
+            for (int i1 = 0; i1 < 3; i1 += 2)
+#pragma unroll
+              for (int i0 = 0; i0 < 3; i0 += 2)
+                if ((g[1 + 2 * s3] >> (i0 + 3 * i1)) & 1u)
+                {
+                  const int o = i0 + 3 * i1 + (NL >= 2 ? SB * (s3 ? 1 : 2 * c3) : 0);
+                  Lf[boff[1 + 2 * s3] + i0 + 3 * i1] = 0.5 * (Lf[o] + Lf[o + 2 * SA]);
+                }
+        }
+        __syncwarp();
+      }
+      if (hangfam)
+      {
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+          for (int i0 = 0; i0 < 3; i0 += 2)
+            if ((g[sg] >> (i0 + 3)) & 1u) Lf[boff[sg] + i0 + 3] = 0.5 * (Lf[boff[sg] + i0] + Lf[boff[sg] + i0 + 6]);
+      }
+      __syncwarp();
+      if (hangfam)
+      {
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+          for (int i1 = 0; i1 < 3; i1++)
+            if ((g[sg] >> (1 + 3 * i1)) & 1u) Lf[boff[sg] + 1 + 3 * i1] = 0.5 * (Lf[boff[sg] + 3 * i1] + Lf[boff[sg] + 2 + 3 * i1]);
+      }
+      __syncwarp();
+    }
+
+    // ---- Q: the quad's 4 children
+    double acc[9 * NS];
+#pragma unroll
+    for (int cq = 0; cq < 4; cq++)
+    {
+      const int c0 = cq & 1, c1 = cq >> 1;
+      double e[N];
+#pragma unroll
+      for (int r = 0; r < N; r++) e[r] = Lf[boff[r >> 2] + (c0 + (r & 1)) + 3 * (c1 + ((r >> 1) & 1))];
+      if (OPKIND == OP_HADAMARD)
+      {
+        wht<N>(e);
+#pragma unroll
+        for (int i = 0; i < N; i++) e[i] *= p.K[i];
+        wht<N>(e);
+      }
+      if (hangfam)
+      {
+        // quirk Q1 on a family (see k_family_check): tau = sum over the child's hanging ranks of 2^-|odd| eout, off its corner
+        double tk[DIM] = {};  // sums of the hanging ranks with 1, 2, .. odd coordinates (the centre, all odd, never hangs)
+#pragma unroll
+        for (int r = 0; r < N; r++)
+        {
+          const int i0 = c0 + (r & 1), i1 = c1 + ((r >> 1) & 1), sg = r >> 2;
+          const int nodd = (i0 == 1) + (i1 == 1) + (sg & 1) + (sg >> 1);
+          if (nodd == 0 || nodd == DIM) continue;  // the corner itself
+          add_if(tk[nodd - 1], e[r], (g[sg] >> (i0 + 3 * i1)) & 1u);
+        }
+        double tau = 0.0;
+#pragma unroll
+        for (int k = DIM - 2; k >= 0; k--) tau = fma(1.0 / (double)(2 << k), tk[k], tau);
+        e[c0 | (c1 << 1)] -= tau;
+      }
+#pragma unroll
+      for (int r = 0; r < N; r++)
+      {
+        const int r0 = r & 1, r1 = (r >> 1) & 1;
+        const int a = (c0 + r0) + 3 * (c1 + r1) + 9 * (r >> 2);
+        if ((c0 == 0 || r0 == 1) && (c1 == 0 || r1 == 1)) acc[a] = e[r];  // first child that touches the point
+        else acc[a] += e[r];
+      }
+    }
+    // the middle points of the lane dimensions are shared with the neighbouring quads
+#pragma unroll
+    for (int sg = 1; sg < NS; sg++)
+#pragma unroll
+      for (int i = 0; i < 9; i++)
+      {
+        double v = acc[i + 9 * sg];
+        if (sg & 1) v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (sg & 2) v += __shfl_xor_sync(0xffffffffu, v, 2);
+        acc[i + 9 * sg] = v;
+      }
+    if (hangfam)
+    {
+      // transposed interpolation of the hanging points towards the corners, one dimension at a time
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i1 = 0; i1 < 3; i1++)
+        {
+          const uint32_t hb = (g[sg] >> (1 + 3 * i1)) & 1u;
+          const double h = 0.5 * acc[1 + 3 * i1 + 9 * sg];
+          add_if(acc[0 + 3 * i1 + 9 * sg], h, hb);
+          add_if(acc[2 + 3 * i1 + 9 * sg], h, hb);
+        }
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i0 = 0; i0 < 3; i0++)
+        {
+          const uint32_t hb = (g[sg] >> (i0 + 3)) & 1u;
+          const double h = 0.5 * acc[i0 + 3 + 9 * sg];
+          add_if(acc[i0 + 9 * sg], h, hb);
+          add_if(acc[i0 + 6 + 9 * sg], h, hb);
+        }
+#pragma unroll
+      for (int d = 0; d < NL; d++)
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
+        {
+          if (!((sg >> d) & 1)) continue;
+#pragma unroll
+          for (int i = 0; i < 9; i++) fma_if(acc[i + 9 * (sg ^ (1 << d))], acc[i + 9 * sg], 0.5, (g[sg] >> i) & 1u);
+        }
+    }
+    __syncwarp();  // every lane of the warp has read its lattice points
+    if (act)
+    {
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+      {
+        // a shared point is stored by the quad with c_d == 0
+        if (((sg & 1) && c2) || ((sg & 2) && c3)) continue;
+#pragma unroll
+        for (int i = 0; i < 9; i++) Lf[boff[sg] + i] = acc[i + 9 * sg];
+      }
+    }
+  }
+  __syncthreads();  // B
+
+  // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
+  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.
+  {
+    const uint16_t *cnt = jd + p.jdStride;
+    const int cnt0 = cnt[0];
+    const int c1 = cnt[1], c2n = cnt[2], c3n = cnt[3], j1 = jd[1], j2 = jd[2], j3 = jd[3];  // jdStride >= 8
+    for (int n = tid; n < cnt0; n += TPB)
+    {
+      double a = Ls[inv[n]];  // jd[0] == 0
+      if (n < c1)
+      {
+        a += Ls[inv[j1 + n]];
+        if (n < c2n)
+        {
+          a += Ls[inv[j2 + n]];
+          if (n < c3n)
+          {
+            a += Ls[inv[j3 + n]];
+            for (int k = 4; n < (int)cnt[k]; k++) a += Ls[inv[(int)jd[k] + n]];
+          }
+        }
+      }
+      const uint32_t r = rec[n];
+      if (DIRI && (r & REC_BDY)) continue;
+      if (r & REC_SHARED) atomicAdd(p.out + (r & REC_GID), a);
+      else p.out[r & REC_GID] = a;
+    }
+  }
+}
+
+template <int DIM, int OPKIND, bool DIRI>
+static int launch_family_one(DA &da, const ChunkSet &cs, MvfParams &p)
+{
+  using F = Fam<DIM>;
+  if (cs.spu != F::L || (int)cs.elemsPerChunk != F::UPC) { set_error("internal: family set does not match its kernel"); return DKT_ERR_INVALID; }
+  p.rk16 = cs.d_rk16; p.inv16 = cs.d_inv16; p.jd = cs.d_jd; p.frec = cs.d_frec; p.rec = (const uint32_t *)cs.d_rec; p.nloc = cs.d_nloc;
+  p.node_off = cs.d_node_off;
+  p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.jdStride = cs.jdStride;
+  p.ncap = (cs.maxNloc + 3) & ~3u;
+  const FamSmem<DIM> lay(p.ncap, p.jdStride);
+  auto kern = k_mvf<DIM, OPKIND, DIRI>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  DKT_LAUNCH(kern, cs.nChunks, F::TPB, lay.total, da.cur ? da.cur : da.stream)(p);
+  g_launches++;
+  return DKT_OK;
+}
+
+template <int DIM>
+static int launch_family_dim(DA &da, const ChunkSet &cs, int opkind, bool diri, MvfParams &p)
+{
+  if (opkind == OP_HADAMARD)
+    return diri ? launch_family_one<DIM, OP_HADAMARD, true>(da, cs, p) : launch_family_one<DIM, OP_HADAMARD, false>(da, cs, p);
+  if (opkind == DKT_OP_IDENTITY)
+    return diri ? launch_family_one<DIM, DKT_OP_IDENTITY, true>(da, cs, p) : launch_family_one<DIM, DKT_OP_IDENTITY, false>(da, cs, p);
+  set_error("internal: no sibling-family kernel for this operator");
+  return DKT_ERR_UNSUPPORTED;
+}
+
+int launch_family_set(DA &da, const ChunkSet &cs, int opkind, bool dirichlet, const double *in, double *out, const double *lscale,
+                      const double *Kdiag)
+{
+  static thread_local MvfParams p;
+  p.in = in;
+  p.out = out;
+  for (int l = 0; l < 32; l++) p.lscale[l] = lscale[l];
+  for (int i = 0; i < 16; i++) p.K[i] = i < (1 << da.dim) ? Kdiag[i] : 0.0;
+  switch (da.dim)
+  {
+  case 2: return launch_family_dim<2>(da, cs, opkind, dirichlet, p);
+  case 3: return launch_family_dim<3>(da, cs, opkind, dirichlet, p);
+  case 4: return launch_family_dim<4>(da, cs, opkind, dirichlet, p);
+  }
+  set_error("unsupported dimension");
+  return DKT_ERR_UNSUPPORTED;
+}
+} // namespace dkt

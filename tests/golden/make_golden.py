@@ -6,8 +6,8 @@
 Each fixture holds, for one seeded case: the input elements, the reference's tree order, its CG
 nodes in DA order (getTNCoords), boundary ids, RefElement's 1-D interpolation matrices, an input
 vector u and v = A u from feMatrix::matVec for (a) the identity elemental operator with u = 1
-(test/testMatvec.cpp:324-399) and (b) a random dense K_ref with level scaling, plus the number of
-eleOp calls.  Hilbert cases also store the reference's SFC tables.
+(test/testMatvec.cpp:324-399), (b) a random dense K_ref with level scaling, (c) order 1: the unit-cell Laplacian
+(--add-laplacian extends existing fixtures in place), plus the number of eleOp calls.  Hilbert cases also store the reference's SFC tables.
 """
 import os
 import sys
@@ -91,10 +91,33 @@ def generate_heatmat(name):
                 v_heat=v_heat, heat_kref=K2 * 2.0 ** (alpha * 2), heat_alpha=alpha, node_xyz=da.nodes()[0])
 
 
+def add_laplacian(name):
+    """Order-1 fixtures also carry v = A u of the reference for the unit-cell Laplacian K_ref (a Walsh-Hadamard-form
+    operator: what the sibling-family kernel serves), K_e = 0.7 h^(dim-2) K_ref, with and without Dirichlet rows."""
+    path = os.path.join(HERE, name + ".npz")
+    g = dict(np.load(path))
+    dim, md = int(g["dim"]), int(g["max_depth"])
+    sfc = "hilbert" if "hilbert" in name else "morton"
+    R = dktref.Reference(dim, md, sfc)
+    tree = R.tree_from_elements(g["in_xyz"], g["in_lev"], sort=True)
+    da = R.da(tree, 1)
+    u = cases.input_vector(da.num_nodes)
+    K = dkt.operators.laplace_kref(dim, 1)
+    g["v_lap"], _, _ = da.matvec(u, dktref.OP_DENSE, K, alpha=dim - 2.0, scale=SCALE)
+    g["v_lap_diri"], _, _ = da.matvec(u, dktref.OP_DENSE, K, alpha=dim - 2.0, scale=SCALE, dirichlet=True)
+    np.savez_compressed(path, **g)
+    print("%-28s + v_lap, v_lap_diri  %6.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
 HEATMAT_CASES = {"heatmat-d3-p1-ball": "ball-d3-p1-morton-6", "heatmat-d3-p1-ex3": "ex3-d3-p1-morton-3"}
 
 
 def main():
+    if "--add-laplacian" in sys.argv:  # extends the committed order-1 fixtures in place
+        for name in cases.ALL_CASES:
+            if "-p1-" in name:
+                add_laplacian(name)
+        return
     for fixture, name in HEATMAT_CASES.items():
         g = generate_heatmat(name)
         path = os.path.join(HERE, fixture + ".npz")
@@ -107,6 +130,8 @@ def main():
         g = generate(case)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **g)
+        if "-p1-" in name and name in cases.ALL_CASES:
+            add_laplacian(name)
         print("%-28s nE=%6d nN=%6d calls=%6d  %6.1f KB" % (name, len(g["elem_lev"]), len(g["node_lev"]), int(g["ncalls"]),
                                                             os.path.getsize(path) / 1024))
 
