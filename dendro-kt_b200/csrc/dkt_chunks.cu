@@ -354,7 +354,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, con
     {
       const uint64_t cbase = c * (uint64_t)upc * spu;
       rk16[cbase + sv] = (uint16_t)nr;
-      if (key[i] != INVALID) inv16[cbase + pos] = (uint16_t)(el * fam_S(fam) + fam_laddr(fam, q));  // every family slot writes
+      if (key[i] != INVALID) inv16[cbase + pos] = (uint16_t)(8 * (el * fam_S(fam) + fam_laddr(fam, q)));  // byte offset; every family slot writes
     }
     if (key[i] != INVALID && head[i])
     {
@@ -368,7 +368,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, con
         gid_out[noff + nr] = key[i];
         meta_out[noff + nr] = (uint16_t)m;
       }
-      else rec_out[noff + nr] = key[i] | ((m & META_SHARED) ? REC_SHARED : 0u) | ((m & META_BDY) ? REC_BDY : 0u);
+      else rec_out[noff + nr] = (key[i] << 2) | ((m & META_SHARED) ? REC_SHARED : 0u) | ((m & META_BDY) ? REC_BDY : 0u);
     }
   }
 }
@@ -1055,7 +1055,9 @@ int build_chunks(DA &da)
   int dev = 0;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&da.numSMs, cudaDevAttrMultiProcessorCount, dev));
-  da.mvStreams = 1;
+  // the sets of one matvec are independent (nodes shared between sets are accumulated with RED): the small per-element sets
+  // of a family DA run beside the family kernel on their own streams
+  da.mvStreams = da.families ? 3 : 1;
   if (const char *e = getenv("DKT_MV_STREAMS")) da.mvStreams = std::max(1, std::min(atoi(e), DA::MAX_AUX + 1));
   if (da.mvStreams > 1 && !da.ev_fork)
   {

@@ -25,7 +25,7 @@
 namespace dkt
 {
 #ifndef DKT_FAM_MINB
-#define DKT_FAM_MINB 3   // resident CTAs per SM the family kernel is compiled for
+#define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
 
 struct MvfParams
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
   {
     const uint32_t r = rec[n];
     if (DIRI && (r & REC_BDY)) un[n] = 0.0;
-    else cp_async8(un + n, p.in + (r & REC_GID));
+    else cp_async8(un + n, p.in + (r >> 2));
   }
   if (tid == 0) un[nloc] = 0.0;  // what the slots without a node read
   cp_async_commit();
@@ -209,17 +209,20 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     // ---- F: fill the family's lattice.  A point with (s2, s3) is shared by the 2^|s| quads that differ in those dimensions;
     // they take its 9 (i0, i1) in turn (static, predicated code: no index arithmetic).
     {
-      const double sc = OPKIND != DKT_OP_IDENTITY ? p.lscale[fr[3] & 31u] : 1.0;
-      if (act)
+      // real points: the lanes of the warp take the nfw * L lattice slots of its families in turn (coalesced rk16 reads, no idle
+      // lanes); slot i = f * L + k goes to Ls[f * S + laddr(k)].  A hanging point reads the chunk's zero entry.  The level
+      // scale is applied to the output lattice instead (the operator is linear).
       {
-#pragma unroll
-        for (int sg = 0; sg < NS; sg++)
+        int k = lane, fo = fw0 * S;  // lane < 32 <= L + 23: at most one wrap per step
+        if (L < 32 && k >= L) { k -= L; fo += S; if (k >= L) { k -= L; fo += S; } if (k >= L) { k -= L; fo += S; } }
+        const uint16_t *rkw = rk + fw0 * L;
+        for (int i = lane; i < nfw * L; i += 32)
         {
-          const int nsh = (sg == 0 ? 1 : sg == 3 ? 4 : 2);
-          const int me = (sg == 0 ? 0 : sg == 1 ? c2 : sg == 2 ? c3 : j);
-#pragma unroll
-          for (int i = 0; i < 9; i++)
-            if (nsh == 1 || (i % nsh) == me) Lf[boff[sg] + i] = un[rkf[kb[sg] + i]] * sc;  // a hanging point reads the zero entry
+          const int q3 = DIM == 4 ? (k * 19) >> 9 : 0;                   // k / 27
+          const int q2 = DIM >= 3 ? ((k - 27 * q3) * 57) >> 9 : 0;       // (k / 9) % 3
+          Ls[fo + k + (SA - 9) * q2 + (SB - 27) * q3] = un[rkw[i]];
+          k += 32;
+          while (k >= L) { k -= L; fo += S; }
         }
       }
       __syncwarp();
@@ -281,14 +284,22 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     }
 
     // ---- Q: the quad's 4 children
-    double acc[9 * NS];
+    // Every lattice point is loaded ONCE, by the first child that touches it, and stays in a register until the last one has
+    // used it (all indices are static: the live set peaks at the last child, where it is empty).
+    double acc[9 * NS], lat[9 * NS];
 #pragma unroll
     for (int cq = 0; cq < 4; cq++)
     {
       const int c0 = cq & 1, c1 = cq >> 1;
       double e[N];
 #pragma unroll
-      for (int r = 0; r < N; r++) e[r] = Lf[boff[r >> 2] + (c0 + (r & 1)) + 3 * (c1 + ((r >> 1) & 1))];
+      for (int r = 0; r < N; r++)
+      {
+        const int r0 = r & 1, r1 = (r >> 1) & 1;
+        const int a = (c0 + r0) + 3 * (c1 + r1) + 9 * (r >> 2);
+        if ((c0 == 0 || r0 == 1) && (c1 == 0 || r1 == 1)) lat[a] = Lf[boff[r >> 2] + (c0 + r0) + 3 * (c1 + r1)];
+        e[r] = lat[a];
+      }
       if (OPKIND == OP_HADAMARD)
       {
         wht<N>(e);
@@ -369,6 +380,12 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     __syncwarp();  // every lane of the warp has read its lattice points
     if (act)
     {
+      if (OPKIND != DKT_OP_IDENTITY)
+      {
+        const double sc = p.lscale[fr[3] & 31u];
+#pragma unroll
+        for (int i = 0; i < 9 * NS; i++) acc[i] *= sc;
+      }
 #pragma unroll
       for (int sg = 0; sg < NS; sg++)
       {
@@ -382,31 +399,39 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
   __syncthreads();  // B
 
   // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
-  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.
+  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.  Four nodes per thread
+  // at a time: independent chains, one jd[k] / cnt[k] load for the four.  inv16 holds BYTE offsets into Ls.
   {
     const uint16_t *cnt = jd + p.jdStride;
     const int cnt0 = cnt[0];
-    const int c1 = cnt[1], c2n = cnt[2], c3n = cnt[3], j1 = jd[1], j2 = jd[2], j3 = jd[3];  // jdStride >= 8
-    for (int n = tid; n < cnt0; n += TPB)
+    const char *Lb = (const char *)Ls;
+    for (int base = tid; base < cnt0; base += 4 * TPB)
     {
-      double a = Ls[inv[n]];  // jd[0] == 0
-      if (n < c1)
+      double a[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
       {
-        a += Ls[inv[j1 + n]];
-        if (n < c2n)
-        {
-          a += Ls[inv[j2 + n]];
-          if (n < c3n)
-          {
-            a += Ls[inv[j3 + n]];
-            for (int k = 4; n < (int)cnt[k]; k++) a += Ls[inv[(int)jd[k] + n]];
-          }
-        }
+        const int n = base + i * TPB;
+        a[i] = n < cnt0 ? *(const double *)(Lb + inv[n]) : 0.0;  // jd[0] == 0
       }
-      const uint32_t r = rec[n];
-      if (DIRI && (r & REC_BDY)) continue;
-      if (r & REC_SHARED) atomicAdd(p.out + (r & REC_GID), a);
-      else p.out[r & REC_GID] = a;
+      for (int k = 1; base < (int)cnt[k]; k++)
+      {
+        const int off = (int)jd[k] + base, ck = (int)cnt[k];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (base + i * TPB < ck) a[i] += *(const double *)(Lb + inv[off + i * TPB]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+      {
+        const int n = base + i * TPB;
+        if (n >= cnt0) continue;
+        const uint32_t r = rec[n];
+        if (DIRI && (r & REC_BDY)) continue;
+        double *dst = p.out + (r >> 2);
+        if (r & REC_SHARED) atomicAdd(dst, a[i]);
+        else *dst = a[i];
+      }
     }
   }
 }
