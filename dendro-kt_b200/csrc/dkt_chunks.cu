@@ -354,6 +354,8 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, con
     {
       const uint64_t cbase = c * (uint64_t)upc * spu;
       rk16[cbase + sv] = (uint16_t)nr;
+      // what the kernel gathers for the lattice slot: node id << 2 | boundary bit, or SLOTW_ABSENT (a hanging point)
+      slot[cbase + sv] = key[i] != INVALID ? ((key[i] << 2) | (isbdy[key[i]] ? SLOTW_BDY : 0u)) : SLOTW_ABSENT;
       if (key[i] != INVALID) inv16[cbase + pos] = (uint16_t)(8 * (el * fam_S(fam) + fam_laddr(fam, q)));  // byte offset; every family slot writes
     }
     if (key[i] != INVALID && head[i])
@@ -446,6 +448,8 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   else
   {
     CK(cudaMalloc((void **)&cs.d_rk16, nslotsAll * sizeof(uint16_t)));
+    CK(cudaMalloc((void **)&cs.d_slot, nslotsAll * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(cs.d_slot, 0xFF, nslotsAll * sizeof(uint32_t), da.stream));  // padding slots: absent
     CK(cudaMalloc((void **)&cs.d_inv16, nslotsAll * sizeof(uint16_t)));
     CK(cudaMalloc((void **)&cs.d_rec, std::max<uint64_t>(total, 4) * sizeof(uint32_t)));
     // bytes the kernel's bulk copies read but the build does not write (tail of the last chunk, padding records)

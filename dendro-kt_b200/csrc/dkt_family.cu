@@ -24,6 +24,9 @@
 
 namespace dkt
 {
+#ifndef DKT_FAM_DIRECT
+#define DKT_FAM_DIRECT 1   // 1: node values are gathered straight into the lattices; 0: staged per chunk node (un[]) and copied
+#endif
 #ifndef DKT_FAM_MINB
 #define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
@@ -33,7 +36,7 @@ struct MvfParams
   const double *in;
   double *out;
   const uint16_t *rk16, *inv16, *jd;
-  const uint32_t *frec, *rec, *nloc;
+  const uint32_t *frec, *rec, *nloc, *slotw;
   const uint64_t *node_off;
   uint32_t nSet, nChunks, jdStride, ncap;  // ncap: multiple of 4, >= the largest chunk's padded node count
   double lscale[32];
@@ -109,9 +112,9 @@ struct FamSmem
   __host__ __device__ FamSmem(uint32_t ncap, uint32_t jdStride)
   {
     uint32_t o = F::UPC * F::S * 8;
-    oUn = o; o += (ncap + 2) * 8;
+    oUn = o; o += DKT_FAM_DIRECT ? 0 : (ncap + 2) * 8;
     oRec = o; o += ncap * 4;
-    oRk = o; o += F::UPC * F::L * 2;
+    oRk = o; o += F::UPC * F::L * (DKT_FAM_DIRECT ? 4 : 2);  // direct: the slot words
     oInv = o; o += F::UPC * F::L * 2;
     oFrec = o; o += F::UPC * 16;
     oJd = o; o += 2 * jdStride * 2;
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
   const uint32_t recBytes = (uint32_t)((nloc + 3) & ~3) * 4u;
 
   // ---- L0: bulk copies of the chunk's tables
+  const uint32_t slotBytes = UPC * L * 2, frecBytes = UPC * 16, jdBytes = 2 * p.jdStride * 2;
   if (tid == 0)
   {
     mbar_init(bar, 1);
@@ -155,11 +159,25 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     mbar_init_fence();
   }
   __syncthreads();
+#if DKT_FAM_DIRECT
+  uint32_t *slw = (uint32_t *)rk;
+  if (tid == 0)
+  {
+    mbar_expect_tx(bar, 2 * slotBytes + frecBytes);
+    bulk_g2s(slw, p.slotw + (uint64_t)c * (UPC * L), 2 * slotBytes, bar);
+    bulk_g2s(frec, p.frec + (uint64_t)c * (UPC * 4), frecBytes, bar);
+    mbar_expect_tx(bar + 1, recBytes + slotBytes + jdBytes);
+    bulk_g2s(rec, p.rec + noff, recBytes, bar + 1);
+    bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
+    bulk_g2s(jd, p.jd + (uint64_t)c * (2 * p.jdStride), jdBytes, bar + 1);
+  }
+  (void)un;
+  mbar_wait(bar, 0);  // slot words and family records
+#else
   if (tid == 0)
   {
     mbar_expect_tx(bar, recBytes);
     bulk_g2s(rec, p.rec + noff, recBytes, bar);
-    const uint32_t slotBytes = UPC * L * 2, frecBytes = UPC * 16, jdBytes = 2 * p.jdStride * 2;
     mbar_expect_tx(bar + 1, 2 * slotBytes + frecBytes + jdBytes);
     bulk_g2s(rk, p.rk16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
     bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
@@ -179,6 +197,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
   mbar_wait(bar + 1, 0);
   cp_async_wait_all();
   __syncthreads();  // A
+#endif
 
   const int fw0 = warp * FPW;
   const int nfw = min(FPW, nfam - fw0);  // families of this warp
@@ -209,21 +228,52 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     // ---- F: fill the family's lattice.  A point with (s2, s3) is shared by the 2^|s| quads that differ in those dimensions;
     // they take its 9 (i0, i1) in turn (static, predicated code: no index arithmetic).
     {
-      // real points: the lanes of the warp take the nfw * L lattice slots of its families in turn (coalesced rk16 reads, no idle
-      // lanes); slot i = f * L + k goes to Ls[f * S + laddr(k)].  A hanging point reads the chunk's zero entry.  The level
-      // scale is applied to the output lattice instead (the operator is linear).
+      // real points.  A lane keeps the same lattice points k (at most KT of them: k0, k0 + 32, ..) for every family of the warp,
+      // so the lattice address is computed once; the table reads of a family are coalesced.  Direct: one 8-byte cp.async per
+      // slot, global -> lattice (a boundary node under Dirichlet rows gets 0, a hanging point is left to the passes below); no
+      // barrier - the warp fills only its own families.  The level scale is applied to the output lattice instead (the
+      // operator is linear).
       {
-        int k = lane, fo = fw0 * S;  // lane < 32 <= L + 23: at most one wrap per step
-        if (L < 32 && k >= L) { k -= L; fo += S; if (k >= L) { k -= L; fo += S; } if (k >= L) { k -= L; fo += S; } }
-        const uint16_t *rkw = rk + fw0 * L;
-        for (int i = lane; i < nfw * L; i += 32)
+        constexpr int FPI = L >= 32 ? 1 : 32 / L;  // families per sweep of the warp
+        constexpr int KT = (L + 31) / 32;          // lattice points per lane
+        const int fsub = L >= 32 ? 0 : lane / L, k0 = L >= 32 ? lane : lane % L;
+        int la[KT];
+#pragma unroll
+        for (int t = 0; t < KT; t++)
         {
-          const int q3 = DIM == 4 ? (k * 19) >> 9 : 0;                   // k / 27
-          const int q2 = DIM >= 3 ? ((k - 27 * q3) * 57) >> 9 : 0;       // (k / 9) % 3
-          Ls[fo + k + (SA - 9) * q2 + (SB - 27) * q3] = un[rkw[i]];
-          k += 32;
-          while (k >= L) { k -= L; fo += S; }
+          const int k = min(k0 + 32 * t, L - 1);
+          la[t] = fam_laddr(DIM, k);
         }
+#if DKT_FAM_DIRECT
+        const uint32_t *sww = slw + fw0 * L;
+#else
+        const uint16_t *rkw = rk + fw0 * L;
+#endif
+        if (fsub < FPI)
+          for (int fl2 = fsub; fl2 < nfw; fl2 += FPI)
+          {
+#pragma unroll
+            for (int t = 0; t < KT; t++)
+            {
+              const int k = k0 + 32 * t;
+              if (k >= L) continue;
+              double *dst = Ls + (fw0 + fl2) * S + la[t];
+#if DKT_FAM_DIRECT
+              const uint32_t w = sww[fl2 * L + k];
+              if (!(w & SLOTW_ABSENT))
+              {
+                if (DIRI && (w & SLOTW_BDY)) *dst = 0.0;
+                else cp_async8(dst, p.in + (w >> 2));
+              }
+#else
+              *dst = un[rkw[fl2 * L + k]];
+#endif
+            }
+          }
+#if DKT_FAM_DIRECT
+        cp_async_commit();
+        cp_async_wait_all();
+#endif
       }
       __syncwarp();
       // Hanging points: exact order-1 interpolation from the corners of G(p), one dimension at a time - the points whose LOWEST
@@ -396,6 +446,9 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
       }
     }
   }
+#if DKT_FAM_DIRECT
+  mbar_wait(bar + 1, 0);
+#endif
   __syncthreads();  // B
 
   // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
@@ -442,7 +495,7 @@ static int launch_family_one(DA &da, const ChunkSet &cs, MvfParams &p)
   using F = Fam<DIM>;
   if (cs.spu != F::L || (int)cs.elemsPerChunk != F::UPC) { set_error("internal: family set does not match its kernel"); return DKT_ERR_INVALID; }
   p.rk16 = cs.d_rk16; p.inv16 = cs.d_inv16; p.jd = cs.d_jd; p.frec = cs.d_frec; p.rec = (const uint32_t *)cs.d_rec; p.nloc = cs.d_nloc;
-  p.node_off = cs.d_node_off;
+  p.node_off = cs.d_node_off; p.slotw = cs.d_slot;
   p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.jdStride = cs.jdStride;
   p.ncap = (cs.maxNloc + 3) & ~3u;
   const FamSmem<DIM> lay(p.ncap, p.jdStride);

@@ -43,6 +43,7 @@ struct ChunkSet
   uint32_t nChunks = 0, elemsPerChunk = 0, maxNloc = 0, maxLen = 0, jdStride = 0;
   uint64_t totalNodes = 0;
   uint32_t *d_slot = nullptr;    // [nChunks*elemsPerChunk*rows*N] node rank | position << 16, rank-major per chunk
+                                 // (family sets: [nChunks*upc*spu] node id << 2 | boundary bit, or "absent", unit-major)
   uint32_t *d_gid = nullptr;     // [totalNodes] global node id, chunk by chunk, (len desc) order inside a chunk
   uint16_t *d_meta = nullptr;    // [totalNodes] run length | boundary bit | shared bit
   uint16_t *d_jd = nullptr;      // [nChunks*jdStride] jagged-diagonal offsets
