@@ -33,6 +33,72 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def kernel_source_sha():
+    """sha256 (16 hex digits) over the CUDA sources of the matvec path: keys the ncu-measured traffic in profiles/."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "dendro-kt_b200", "csrc")
+    for f in ("dkt_family.cu", "dkt_chunks.cu", "dkt_chunks.h", "dkt_dist.cu", "dkt_p2p.cuh"):
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(n_elem):
+    """DRAM bytes per matvec step from the committed ncu capture (profiles/traffic.json, written by tools/ncu_traffic.py):
+    used only if it was taken with the same kernel sources on the same workload; None otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t.get("kernel_source_sha") == kernel_source_sha() and int(t.get("n_elem", -1)) == int(n_elem):
+            return float(t["dram_bytes_per_step"])
+    except Exception:
+        pass
+    return None
+
+
+GOLDEN_PARITY_CASES = ("ball-d4-p1-morton-5", "gauss-d4-p1-morton")
+
+
+def golden_parity(dkt, rank, world, dist, bcast_id):
+    """The bench's own DA path (partitioned when world > 1) on committed golden fixtures taken from the reference
+    (tests/golden/*.npz, tests/golden/make_golden.py): v = A u for the unit-cell Laplacian (family kernel + singles) and a
+    general dense operator (per-element kernels), gathered to the single-rank node order and compared with the reference's
+    vectors.  Returns the worst relative error per case; the caller fails the run above 1e-12."""
+    import numpy as np
+    import torch
+    from dkt import operators
+    out = []
+    for name in GOLDEN_PARITY_CASES:
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        dim, md = int(g["dim"]), int(g["max_depth"])
+        kw = dict(ip0=g["ip0"], ip1=g["ip1"])
+        if world > 1:
+            kw.update(rank=rank, nranks=world, nccl_id=bcast_id())
+        da = dkt.DA(g["in_xyz"], g["in_lev"], dim, 1, md, **kw)
+        n = len(g["node_lev"])
+        u = np.random.default_rng(99).uniform(-1.0, 1.0, n)  # the fixtures' input vector (tests/cases.py input_vector)
+        worst = 0.0
+        N = 1 << dim
+        Kd = np.random.default_rng(5).uniform(-1.0, 1.0, (N, N))  # the fixtures' dense operator (tests/cases.py dense_operator)
+        for op, scale, want in ((dkt.Operator.dense(operators.laplace_kref(dim, 1), dim - 2.0), 0.7, g["v_lap"]),
+                                (dkt.Operator.dense(operators.laplace_kref(dim, 1), dim - 2.0, dirichlet=True), 0.7, g["v_lap_diri"]),
+                                (dkt.Operator.dense(Kd, float(g["alpha"])), float(g["scale"]), g["v_dense"])):
+            if world > 1:
+                ids = torch.from_numpy(da.owned_ids().astype(np.int64)).cuda()
+                v_loc = da.matvec(op, torch.from_numpy(u).cuda()[ids].contiguous(), scale=scale)
+                torch.cuda.synchronize()  # the DA works on its own stream
+                full = torch.zeros(n, dtype=torch.float64, device="cuda")
+                full[ids] = v_loc
+                dist.all_reduce(full)
+                v = full.cpu().numpy()
+            else:
+                v = da.matvec(op, u, scale=scale)
+            worst = max(worst, float(np.abs(v - want).max() / np.abs(want).max()))
+        out.append({"case": name, "max_rel_err": worst})
+        da.close()
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -116,8 +182,20 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dkt
+    import dktref
+    import flat
+    if not dktref.available("morton"):
+        raise SystemExit("oracle/_ref is not built (python __graft_entry__.py in the build container)")
+    dktref._lib("morton")  # mapped in THIS process too (the workers are forked from it)
     procs = args.ref_procs if args.ref_procs > 0 else max(1, min(os.cpu_count() or 1, 64))
-    level = 5
+    level = args.ref_level
+    # workload facts of the sample, from the oracle's table construction (CPU, numpy)
+    sx, sl = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH)
+    st = flat.build_tables(sx, sl, DIM, ORDER, MAX_DEPTH)
+    n_hang, tree_class = int(len(st.hang_idx)), st.tree_class
+    del sx, sl, st
     ctx = mp.get_context("fork")
     barrier = ctx.Barrier(procs)
     out = ctx.Queue()
@@ -137,8 +215,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "4D p=1 Laplacian matvec, space-time moving-ball adaptive tree (class B), CPU sample", "dim": DIM,
-                   "order": ORDER, "n_elem": n_elem, "n_nodes": n_nodes, "replicas": procs},
+        "config": {"workload": "4D p=1 Laplacian matvec (K_e = h^2 K_ref), space-time moving-ball adaptive tree, class B, max_level %d of "
+                               "max_depth %d: the bench tree's generator at the largest level the reference builds and runs within about "
+                               "a minute per core" % (level, MAX_DEPTH),
+                   "dim": DIM, "order": ORDER, "n_elem": n_elem, "n_nodes": n_nodes, "n_hanging_elem": n_hang, "tree_class": tree_class,
+                   "replicas": procs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -190,6 +271,20 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t)
 
+    def bcast_id():
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(dkt.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return idt.cpu().numpy().tobytes()
+
+    # ---- parity first: the same DA path on golden fixtures taken from the reference (all ranks take part) ----
+    parity = golden_parity(dkt, rank, world, dist, bcast_id)
+    if any(not (c["max_rel_err"] <= 1e-12) for c in parity):
+        if rank == 0:
+            print(json.dumps({"error": "parity check against the reference's golden vectors failed", "dist_parity": parity, "tol": 1e-12}))
+        raise SystemExit(3)
+
     # ---- the tree: identical on every rank (weak scaling: the ball's time window grows with N) ----
     level = args.level
     width = weak_window(world, args.per_gpu_elems) if level == 9 else 0.5
@@ -199,11 +294,7 @@ def run_gpu(args):
     t_tree = time.time() - t0
     t0 = time.time()
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(dkt.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH, rank=rank, nranks=world, nccl_id=idt.cpu().numpy().tobytes())
+        da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH, rank=rank, nranks=world, nccl_id=bcast_id())
     else:
         da = dkt.DA(xyz, lev, DIM, ORDER, MAX_DEPTH)
     t_build = time.time() - t0
@@ -294,13 +385,17 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # ncu dram__bytes_read+write of the step's kernels on the default workload (profiles/README.md);
                          # None for other workloads
-                         "traffic": None,
+                         "traffic": measured_traffic(n_elem_global) if world == 1 else None,
+                         "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write over one step, same kernel sources)",
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                          "alg_bytes_per_step_per_gpu": alg_total / world,
                          "kernel": "whole matvec step per GPU (memset + family kernel + per-element kernels of the singles" +
                                    (" + ghost pack/NCCL/unpack)" if world > 1 else ")")},
             "e2e": {"value": n_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n_global, "d2h_bytes_per_step": 8 * n_global,
                     "ms_per_step": e2e_s * 1e3, "max_rel_diff_vs_device_path": check},
+            "dist_parity": {"cases": parity, "tol": 1e-12, "ranks": world,
+                            "what": "Laplacian (+ Dirichlet) and dense-operator matvec of this DA path on golden fixtures from the reference, "
+                                    "gathered to the single-rank node order"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "ms_per_step_min_max_rank0": [min(per_step), max(per_step)],
@@ -308,7 +403,7 @@ def run_gpu(args):
         }
         if args.cpu_baseline and world == 1:
             try:
-                cv, cs, sample, _, _ = cpu_reference_run(5, 2)
+                cv, cs, sample, _, _ = cpu_reference_run(10, 10)
                 line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample}
             except Exception as e:  # the bench line must survive a missing oracle
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
@@ -328,6 +423,7 @@ def main():
     ap.add_argument("--per-gpu-elems", type=float, default=1.2e7, help="weak scaling: target elements per GPU (level 9)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: replicas (0 = one per core, at most 64)")
+    ap.add_argument("--ref-level", type=int, default=6, help="--impl reference: finest level of the sample tree (6: 6.5e5 elements, 36 %% hanging)")
     ap.add_argument("--families", type=int, default=None, choices=[0, 1],
                     help="0: per-element chunk tables only (DKT_FAMILIES=0); default: sibling-family tables")
     args = ap.parse_args()

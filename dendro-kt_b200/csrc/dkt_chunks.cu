@@ -56,8 +56,8 @@
 // (FEM/include/matvec.h:517) are read-only (node rank but no position, not counted in the run length);
 // one 32-bit mask per element tells which own slots are filled.  Semantics are those of dkt_matvec.cu
 // (reference: FEM/include/matvec.h:378-522); the Q1-free variant runs on the flat kernels.
-// Partitioned DAs build three phases of sets (interior first half / boundary / interior second half)
-// so that dkt_dist.cu can run the ghost exchanges beside the interior elements.
+// Partitioned DAs build two phases of sets (interior / boundary = touches a ghost node) so that dkt_dist.cu can run the
+// ghost exchanges and the boundary elements beside the interior ones.
 //
 // This file also compiles under -DDKT_EMU with tests/emu/cuda_emu.h (fibers on the CPU) - that build exists
 // ONLY so the CPU test-suite can execute the table construction and the kernels' logic against the oracle;
@@ -218,6 +218,37 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, con
   if (lastvalid) atomicMax(&s_P, lastvalid);
   uint16_t rank0[ITEMS];
   {
+    int rk = before - 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      if (head[i])
+      {
+        rk++;
+        s_start[rk] = (uint16_t)(threadIdx.x * ITEMS + i);
+      }
+      rank0[i] = (uint16_t)(rk < 0 ? 0 : rk);
+    }
+  }
+  if (fam)
+  {
+    // Family sets: a run longer than FAM_MAXRUN is cut into pieces, each a chunk node of its own with the same global id (the
+    // pieces are accumulated with RED like a node shared between chunks).  The kernel's node phase then needs at most
+    // FAM_MAXRUN dependent steps per node instead of up to 2^dim.  Heads of the pieces: every FAM_MAXRUN-th reference.
+    __syncthreads();
+    nheads = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++)
+    {
+      if (key[i] != INVALID)
+      {
+        const int kidx = threadIdx.x * ITEMS + i - (int)s_start[rank0[i]];
+        head[i] = (kidx % FAM_MAXRUN) == 0;
+      }
+      nheads += head[i];
+    }
+    __syncthreads();
+    Scan(tmp.scan).ExclusiveSum(nheads, before, total);
     int rk = before - 1;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++)
@@ -908,8 +939,8 @@ static int finish_sets(DA &da, std::vector<ChunkSet> &sets, std::vector<PendingS
   return rc;
 }
 
-// per-element sets of all visited elements: one regular + one hanging set, or (partitioned) three phases of each:
-// interior first half / boundary / interior second half - see run_matvec_dist
+// per-element sets of all visited elements: one regular + one hanging set, or (partitioned) two phases of each:
+// interior (phase 0) / boundary = touches a ghost node (phase 1) - see run_matvec_dist
 static int build_elem_sets(DA &da, std::vector<ChunkSet> &sets)
 {
   const int N = da.N;
@@ -920,8 +951,8 @@ static int build_elem_sets(DA &da, std::vector<ChunkSet> &sets)
   if (da.phased)
   {
     const uint64_t ri = da.nRegInterior, hi = da.nHangInterior;
-    rr = {{0, ri / 2, 0}, {ri, da.nReg, 1}, {ri / 2, ri, 2}};
-    hr = {{0, hi / 2, 0}, {hi, da.nHang, 1}, {hi / 2, hi, 2}};
+    rr = {{0, ri, 0}, {ri, da.nReg, 1}};
+    hr = {{0, hi, 0}, {hi, da.nHang, 1}};
   }
   else
   {
@@ -994,14 +1025,8 @@ static int build_family_sets(DA &da, std::vector<ChunkSet> &sets)
       temps.push_back(frec);
       DKT_LAUNCH(k_family_gather, nblk(nFam * L), 256, 0, da.stream)(fflag, fpos, nFam, da.dim, mem, da.d_mv_lev, Uall, hm, Uc, frec);
       g_launches++;
-      // interior families run in two halves around the boundary ones (see run_matvec_dist); unpartitioned: one set
-      struct Sub { uint64_t a, b; int phase; };
-      std::vector<Sub> subs;
-      if (!phased) subs = {{0, cnt, 0}};
-      else if (c == 1) subs = {{0, cnt, 1}};
-      else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
-      for (const Sub &sb : subs)
-        if (rc == DKT_OK) rc = add_family_set(da, sets, pend, Uc + sb.a * L, frec + sb.a * 4, sb.b - sb.a, sb.phase);
+      // partitioned: the interior families (phase 0) run beside the exchange + boundary families (phase 1), see run_matvec_dist
+      if (rc == DKT_OK) rc = add_family_set(da, sets, pend, Uc, frec, cnt, (phased && c == 1) ? 1 : 0);
     }
     CK(cudaStreamSynchronize(da.stream));
     cudaFree(fflag);
@@ -1023,13 +1048,7 @@ static int build_family_sets(DA &da, std::vector<ChunkSet> &sets)
     DKT_LAUNCH(k_compact, nblk(n), 256, 0, da.stream)(flag, pos, n, list);
     g_launches++;
     const int hang = (c >> 1) & 1, bdy = c & 1;
-    struct Sub { uint64_t a, b; int phase; };
-    std::vector<Sub> subs;
-    if (!phased) subs = {{0, cnt, 0}};
-    else if (bdy) subs = {{0, cnt, 1}};
-    else subs = {{0, cnt / 2, 0}, {cnt / 2, cnt, 2}};
-    for (const Sub &sb : subs)
-      if (rc == DKT_OK) rc = add_single_set(da, sets, pend, list + sb.a, sb.b - sb.a, hang, sb.phase);
+    if (rc == DKT_OK) rc = add_single_set(da, sets, pend, list, cnt, hang, (phased && bdy) ? 1 : 0);
   }
   CK(cudaStreamSynchronize(da.stream));
   for (void *t : temps) cudaFree(t);

@@ -39,6 +39,7 @@ constexpr uint32_t META_PRESENT = 0x2000u;  // node exists (its run may be empty
 constexpr uint32_t META_BDY = 0x4000u;
 constexpr uint32_t META_SHARED = 0x8000u;
 constexpr uint32_t REC_SHARED = 2u, REC_BDY = 1u;  // family sets: 4-byte node records gid << 2 | shared | boundary
+constexpr int FAM_MAXRUN = 4;               // family sets: longest run of a chunk node (longer ones are cut, see k_chunk_build)
 constexpr uint32_t SLOTW_BDY = 1u, SLOTW_ABSENT = 2u;  // family sets: slot words gid << 2 | flags
 constexpr uint32_t SLOT_RO = 0x80000000u;   // unit slot table: read-only reference (node ids are < 2^31)
 

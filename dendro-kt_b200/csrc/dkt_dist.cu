@@ -288,6 +288,11 @@ int dist_allreduce(Dist &d, double *red, cudaStream_t s)
 
 void free_dist(Dist &d)
 {
+  if (d.timing && d.tcount)
+    fprintf(stderr, "[dkt rank %d] %d overlapped matvecs, min ms from start: ghost values in %.4f, interior done %.4f, boundary done %.4f, end %.4f\n",
+            d.rank, d.tcount, d.tsum[0], d.tsum[1], d.tsum[2], d.tsum[3]);
+  for (int i = 0; i < 5; i++)
+    if (d.tev[i]) cudaEventDestroy(d.tev[i]);
   if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_p)d.comm);
   for (int i = 0; i < 4; i++)
     if (d.ev[i]) cudaEventDestroy(d.ev[i]);
@@ -558,7 +563,7 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   //      run while the ghost exchanges are in flight --------------------------------------------------------------
   // Measured on 8 B200s (profiles/README.md): the split pays at 8 ranks (0.95 vs 1.00 ms) and costs at 2
   // (three kernel pairs instead of one); default: on for more than 2 ranks, DKT_DIST_OVERLAP=0/1 overrides.
-  bool wantOverlap = nranks > 2;
+  bool wantOverlap = nranks > 1;
   if (const char *e = getenv("DKT_DIST_OVERLAP")) wantOverlap = atoi(e) != 0;
   uint64_t nRegInt = nRegL, nHangInt = nHangL;
   for (int pass = 0; pass < 2 && wantOverlap; pass++)
@@ -649,18 +654,47 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
     CK(cudaStreamCreateWithPriority(&dist.comm_stream, cudaStreamNonBlocking, hi));  // exchanges first
   }
   for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&dist.ev[i], cudaEventDisableTiming));
+  if (const char *e = getenv("DKT_DIST_TIMING"))
+    if (atoi(e) != 0)
+    {
+      dist.timing = true;
+      for (int i = 0; i < 5; i++) CK(cudaEventCreate(&dist.tev[i]));
+    }
   dist.active = true;
   return DKT_OK;
 }
 
-// The same protocol over peer memory (DKT_DIST_P2P=1): everything on the DA's stream.
+// run_matvec_chunked of one phase on another stream (the exchange stream): single-stream launch, the DA's aux streams and
+// their events belong to the call on the main stream
+static int chunked_on(DA &da, cudaStream_t st, const dkt_op *op, const double *in, double *out, double scale, unsigned flags,
+                      unsigned phaseMask)
+{
+  cudaStream_t keep = da.stream;
+  const int keepStreams = da.mvStreams;
+  da.stream = st;
+  da.mvStreams = 1;
+  const int rc = run_matvec_chunked(da, op, in, out, scale, flags, phaseMask, false);
+  da.stream = keep;
+  da.mvStreams = keepStreams;
+  return rc;
+}
+
+// Schedule of a partitioned matvec with comm/compute overlap (da.phased), both exchanges:
+//   main stream s:      zero out_local ............ interior elements (one launch per set) ............ join, add what came back
+//   exchange stream cs: (high priority) ghost read -> boundary elements -> ghost write-back
+// The interior elements touch no ghost node, the boundary ones run as soon as the ghost values are there, and both kinds
+// accumulate shared nodes with RED (a node private to one chunk belongs to one set), so the two streams need no ordering
+// between them.  The owners add the returned partial sums after the join: that kernel must not race with plain stores.
+//
+// The peer-memory exchange (DKT_DIST_P2P=1): puts into the peers' buffers + epoch flags instead of NCCL send/recv.
 // `stages` (bit mask) exists for the single-process emulation of several ranks, where a rank cannot wait for a flag
-// another rank has not yet had the chance to raise: 1 = put + signal (+ first interior half), 2 = wait for the ghost
-// values, boundary (or all) elements, write-back put + signal (+ second interior half), 4 = wait + accumulate.
+// another rank has not yet had the chance to raise: 1 = put + signal (+ interior elements), 2 = wait for the ghost
+// values, boundary (or all) elements, write-back put + signal, 4 = wait + accumulate.
 static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double *in_local, double *out_local,
                                double scale, unsigned flags, bool overlap, bool ghosted, unsigned stages = 7u)
 {
   cudaStream_t s = da.stream;
+  cudaStream_t cs = overlap ? d.comm_stream : s;
   const int R = d.nranks;
   const uint64_t nOwned = d.nOwned, totalSend = d.send_off[R], nGhost = d.recv_off[R];
   if (stages & 1u) ++d.epoch;
@@ -670,34 +704,42 @@ static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *
   int rc = DKT_OK;
   if (stages & 1u)
   {
+    if (overlap)
+    {
+      CK(cudaMemsetAsync(out_local, 0, (nOwned + nGhost) * sizeof(double), s));
+      g_launches++;
+      CK(cudaEventRecord(d.ev[0], s));
+      CK(cudaStreamWaitEvent(cs, d.ev[0], 0));
+    }
     // readFromGhost: owned values other ranks ghost -> their xr, then publish the epoch
-    LAUNCHS(k_p2p_put, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
-    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagR, d.d_send_off, R, epoch);
+    LAUNCHS(k_p2p_put, totalSend, cs, d_in, d.d_send_idx, totalSend, d.d_send_off, d.d_peer_xr, R);
+    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, cs)(d.d_peer_flagR, d.d_send_off, R, epoch);
     g_launches++;
     if (overlap)
     {
-      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);  // interior, first half
+      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, false);  // interior elements, on s
       if (rc) return rc;
     }
   }
   if (stages & 2u)
   {
-    LAUNCHS(k_p2p_wait_copy, nGhost, s, flagR, d.d_recv_off, R, epoch, xr, in_local + nOwned, nGhost, d.d_p2p_err);
-    if (overlap) rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
+    LAUNCHS(k_p2p_wait_copy, nGhost, cs, flagR, d.d_recv_off, R, epoch, xr, in_local + nOwned, nGhost, d.d_p2p_err);
+    if (overlap) rc = chunked_on(da, cs, op, in_local, out_local, scale, flags, 1u << 1);  // boundary elements
     else rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
                                     : run_matvec_chunked(da, op, in_local, out_local, scale, flags);
     if (rc) return rc;
-    // writeToGhosts: ghost partial sums -> the owners' xw, publish, then add what came back for the owned nodes
-    LAUNCHS(k_p2p_put, nGhost, s, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
-    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, s)(d.d_peer_flagW, d.d_recv_off, R, epoch);
+    // writeToGhosts: ghost partial sums -> the owners' xw, publish
+    LAUNCHS(k_p2p_put, nGhost, cs, out_local + nOwned, (const uint32_t *)nullptr, nGhost, d.d_recv_off, d.d_peer_xw, R);
+    DKT_DIST_LAUNCH(k_p2p_signal, 1, P2P_MAX_RANKS, cs)(d.d_peer_flagW, d.d_recv_off, R, epoch);
     g_launches++;
     if (overlap)
     {
-      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);  // interior, second half
-      if (rc) return rc;
+      CK(cudaEventRecord(d.ev[3], cs));
+      CK(cudaStreamWaitEvent(s, d.ev[3], 0));
     }
   }
   if (!(stages & 4u)) return DKT_OK;
+  // add what came back for the owned nodes
   LAUNCHS(k_p2p_wait_add, totalSend, s, flagW, d.d_send_off, R, epoch, xw, out_local, d.d_send_idx, totalSend, d.d_p2p_err);
   if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
   if (getenv("DKT_P2P_CHECK"))
@@ -720,7 +762,7 @@ int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in
 {
   cudaStream_t s = da.stream;
   const uint64_t nOwned = d.nOwned;
-  const uint64_t totalSend = d.send_off[d.nranks];
+  const uint64_t totalSend = d.send_off[d.nranks], nGhost = d.recv_off[d.nranks];
   // DKT_VEC_GHOSTED: the caller's vectors already have room for the ghost segment ([owned | ghosts],
   // like the reference's ghosted vectors) and are used in place - no staging copies
   if (da.N > MAX_NPE) flags |= DKT_MV_FLAT;  // 81 nodes per element: flat kernels only (no phases)
@@ -731,16 +773,21 @@ int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in
   const bool overlap = d.nranks > 1 && da.phased && !(flags & DKT_MV_FLAT);
   if (d.p2p && d.nranks > 1) return run_matvec_dist_p2p(da, d, op, d_in, d_out, in_local, out_local, scale, flags, overlap, ghosted, stages);
   if (stages != 7u) { set_error("staged execution exists for the peer-memory exchange only"); return DKT_ERR_INVALID; }
-  cudaStream_t cs = overlap ? d.comm_stream : s;  // the exchanges run beside the interior elements
+  cudaStream_t cs = overlap ? d.comm_stream : s;  // the exchanges and the boundary elements run beside the interior elements
+  int rc = DKT_OK;
+  const bool tm = d.timing && overlap;
+  if (tm) CK(cudaEventRecord(d.tev[0], s));
+  if (overlap)
+  {
+    CK(cudaMemsetAsync(out_local, 0, (nOwned + nGhost) * sizeof(double), s));
+    g_launches++;
+    CK(cudaEventRecord(d.ev[0], s));
+    CK(cudaStreamWaitEvent(cs, d.ev[0], 0));
+  }
   if (d.nranks > 1)
   {
     // readFromGhost: owners -> ghosts, received straight into the ghost segments of the local vector
-    LAUNCHS(k_pack, totalSend, s, d_in, d.d_send_idx, totalSend, d.d_send_buf);
-    if (overlap)
-    {
-      CK(cudaEventRecord(d.ev[0], s));
-      CK(cudaStreamWaitEvent(cs, d.ev[0], 0));
-    }
+    LAUNCHS(k_pack, totalSend, cs, d_in, d.d_send_idx, totalSend, d.d_send_buf);
     NCK(g_nccl.GroupStart());
     for (int p = 0; p < d.nranks; p++)
     {
@@ -751,9 +798,7 @@ int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in
     }
     NCK(g_nccl.GroupEnd());
     g_launches++;
-    if (overlap) CK(cudaEventRecord(d.ev[1], cs));
   }
-  int rc = DKT_OK;
   if (!overlap)
   {
     rc = (flags & DKT_MV_FLAT) ? run_matvec(da, op, in_local, out_local, scale, flags)
@@ -762,14 +807,14 @@ int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in
   }
   else
   {
-    // interior elements (first half) touch no ghost node: they run while the ghost values arrive
-    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, true);
+    // interior elements touch no ghost node: they run on s while the ghost values arrive and the boundary elements run on cs
+    if (tm) CK(cudaEventRecord(d.tev[1], cs));  // ghost values have arrived
+    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 0, false);
     if (rc) return rc;
-    CK(cudaStreamWaitEvent(s, d.ev[1], 0));
-    rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 1, false);  // boundary elements
+    if (tm) CK(cudaEventRecord(d.tev[2], s));   // interior elements done
+    rc = chunked_on(da, cs, op, in_local, out_local, scale, flags, 1u << 1);
     if (rc) return rc;
-    CK(cudaEventRecord(d.ev[2], s));
-    CK(cudaStreamWaitEvent(cs, d.ev[2], 0));
+    if (tm) CK(cudaEventRecord(d.tev[3], cs));  // boundary elements done
   }
   if (d.nranks > 1)
   {
@@ -787,14 +832,24 @@ int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in
     if (overlap)
     {
       CK(cudaEventRecord(d.ev[3], cs));
-      // interior elements (second half) run while the partial sums travel
-      rc = run_matvec_chunked(da, op, in_local, out_local, scale, flags, 1u << 2, false);
-      if (rc) return rc;
       CK(cudaStreamWaitEvent(s, d.ev[3], 0));
     }
     LAUNCHS(k_unpack_add, totalSend, s, out_local, d.d_send_idx, totalSend, d.d_recv_buf);
   }
   if (!ghosted) CK(cudaMemcpyAsync(d_out, out_local, nOwned * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (tm)
+  {
+    CK(cudaEventRecord(d.tev[4], s));
+    CK(cudaEventSynchronize(d.tev[4]));
+    CK(cudaEventSynchronize(d.tev[3]));
+    for (int i = 0; i < 4; i++)
+    {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, d.tev[0], d.tev[i + 1]));
+      d.tsum[i] = d.tcount ? std::min(d.tsum[i], (double)ms) : (double)ms;  // minimum over the calls
+    }
+    d.tcount++;
+  }
   return DKT_OK;
 }
 } // namespace dkt

@@ -27,6 +27,9 @@ namespace dkt
 #ifndef DKT_FAM_DIRECT
 #define DKT_FAM_DIRECT 1   // 1: node values are gathered straight into the lattices; 0: staged per chunk node (un[]) and copied
 #endif
+#ifndef DKT_FAM_EXP
+#define DKT_FAM_EXP 0      // timing experiments only (wrong results): 1 no node phase, 2 no hanging-node code, 4 no operator, 8 no gather, 16 no RED
+#endif
 #ifndef DKT_FAM_MINB
 #define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
       kb[sg] = 9 * p2 + 27 * p3;
       g[sg] = (fr[DIM == 4 ? p3 : 0] >> (9 * p2)) & 0x1FFu;
     }
-    const bool hangfam = act && (fr[0] | fr[1] | fr[2]) != 0u;
+    const bool hangfam = act && (fr[0] | fr[1] | fr[2]) != 0u && !(DKT_FAM_EXP & 2);
 
     // ---- F: fill the family's lattice.  A point with (s2, s3) is shared by the 2^|s| quads that differ in those dimensions;
     // they take its 9 (i0, i1) in turn (static, predicated code: no index arithmetic).
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
               const uint32_t w = sww[fl2 * L + k];
               if (!(w & SLOTW_ABSENT))
               {
-                if (DIRI && (w & SLOTW_BDY)) *dst = 0.0;
+                if ((DIRI && (w & SLOTW_BDY)) || (DKT_FAM_EXP & 8)) *dst = 0.0;
                 else cp_async8(dst, p.in + (w >> 2));
               }
 #else
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
         if ((c0 == 0 || r0 == 1) && (c1 == 0 || r1 == 1)) lat[a] = Lf[boff[r >> 2] + (c0 + r0) + 3 * (c1 + r1)];
         e[r] = lat[a];
       }
-      if (OPKIND == OP_HADAMARD)
+      if (OPKIND == OP_HADAMARD && !(DKT_FAM_EXP & 4))
       {
         wht<N>(e);
 #pragma unroll
@@ -452,38 +455,50 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
   __syncthreads();  // B
 
   // ---- N: the chunk's nodes.  Nodes are ranked by run length (descending) and cnt[k] = #nodes with a run longer than k,
-  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one.  Four nodes per thread
-  // at a time: independent chains, one jd[k] / cnt[k] load for the four.  inv16 holds BYTE offsets into Ls.
+  // so node n has a k-th contribution iff n < cnt[k]; every node of a family chunk has at least one and at most FAM_MAXRUN
+  // (k_chunk_build cuts longer runs into pieces that are chunk nodes of their own).  A thread takes the nodes tid, tid + TPB,
+  // ..., two at a time: their 2 x FAM_MAXRUN index loads go out together, then the value loads - two dependent steps for a
+  // pair of nodes whatever their run lengths.  inv16 holds BYTE offsets into Ls.
   {
+    static_assert(FAM_MAXRUN == 4, "the node phase is written for runs of at most four");
     const uint16_t *cnt = jd + p.jdStride;
-    const int cnt0 = cnt[0];
+    const int cnt0 = (DKT_FAM_EXP & 1) ? 0 : cnt[0];
+    const int cn[4] = {cnt0, (int)cnt[1], (int)cnt[2], (int)cnt[3]};
+    const int jo[4] = {0, (int)jd[1], (int)jd[2], (int)jd[3]};
     const char *Lb = (const char *)Ls;
-    for (int base = tid; base < cnt0; base += 4 * TPB)
+    for (int base = tid; base < cnt0; base += 2 * TPB)
     {
-      double a[4];
+      uint32_t ix[2][4];
+      double v[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-      {
-        const int n = base + i * TPB;
-        a[i] = n < cnt0 ? *(const double *)(Lb + inv[n]) : 0.0;  // jd[0] == 0
-      }
-      for (int k = 1; base < (int)cnt[k]; k++)
-      {
-        const int off = (int)jd[k] + base, ck = (int)cnt[k];
+      for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-          if (base + i * TPB < ck) a[i] += *(const double *)(Lb + inv[off + i * TPB]);
-      }
+        for (int k = 0; k < 4; k++)
+        {
+          const int n = base + h * TPB;
+          ix[h][k] = 0;
+          if (n < cn[k]) ix[h][k] = inv[jo[k] + n];
+        }
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+          const int n = base + h * TPB;
+          v[h][k] = 0.0;
+          if (n < cn[k]) v[h][k] = *(const double *)(Lb + ix[h][k]);
+        }
+#pragma unroll
+      for (int h = 0; h < 2; h++)
       {
-        const int n = base + i * TPB;
+        const int n = base + h * TPB;
         if (n >= cnt0) continue;
+        const double a = (v[h][0] + v[h][1]) + (v[h][2] + v[h][3]);
         const uint32_t r = rec[n];
         if (DIRI && (r & REC_BDY)) continue;
         double *dst = p.out + (r >> 2);
-        if (r & REC_SHARED) atomicAdd(dst, a[i]);
-        else *dst = a[i];
+        if ((r & REC_SHARED) && !(DKT_FAM_EXP & 16)) atomicAdd(dst, a);
+        else *dst = a;
       }
     }
   }
@@ -499,6 +514,7 @@ static int launch_family_one(DA &da, const ChunkSet &cs, MvfParams &p)
   p.nSet = (uint32_t)cs.nElem; p.nChunks = cs.nChunks; p.jdStride = cs.jdStride;
   p.ncap = (cs.maxNloc + 3) & ~3u;
   const FamSmem<DIM> lay(p.ncap, p.jdStride);
+  if (cs.maxLen > (uint32_t)FAM_MAXRUN || p.jdStride < 4) { set_error("internal: family set with runs longer than the kernel handles"); return DKT_ERR_INVALID; }
   auto kern = k_mvf<DIM, OPKIND, DIRI>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
   DKT_LAUNCH(kern, cs.nChunks, F::TPB, lay.total, da.cur ? da.cur : da.stream)(p);

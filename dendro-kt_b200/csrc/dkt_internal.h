@@ -35,7 +35,7 @@ extern uint64_t g_launches;
 struct ChunkSet
 {
   int rows = 1;                  // 1 regular, 2 hanging (per-element sets: slot rows = own + parent lattice)
-  int phase = 0;                 // partitioned DA: 0 interior (first half), 1 boundary, 2 interior (second half)
+  int phase = 0;                 // partitioned DA: 0 interior, 1 boundary (touches a ghost node)
   uint64_t elem0 = 0;            // first visited element of the set (index into d_mv_*, d_e2n)
   uint64_t hang0 = 0;            // hanging sets: first hanging-local element (index into d_pnode, d_fmask)
   int xorperm = 0;               // slot s of an element with child number c holds rank s ^ c (order 1)
@@ -149,6 +149,11 @@ struct Dist
   uint64_t *d_send_off = nullptr, *d_recv_off = nullptr;        // device copies [nranks+1]
   int *d_p2p_err = nullptr;             // set by a wait kernel that timed out
   uint32_t epoch = 0;
+  // DKT_DIST_TIMING=1 (diagnostics): per-call device times of the overlapped schedule, printed when the DA is destroyed
+  bool timing = false;
+  cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double tsum[4] = {0, 0, 0, 0};
+  int tcount = 0;
 };
 int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id);
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);

@@ -72,6 +72,14 @@ def main():
                 print("%-24s ranks=%d owned=%d ghost=%d dirichlet=%d rel err vs reference %.2e" % (name, world, da.n_nodes,
                                                                                                   da.n_ghost_nodes, diri, err))
             ok &= err < 1e-12
+        if case["order"] == 1:  # the sibling-family kernel under a partition: the reference's Laplacian vectors
+            Kl = dkt.operators.laplace_kref(case["dim"], 1)
+            for diri, want in ((False, g["v_lap"]), (True, g["v_lap_diri"])):
+                v = gathered_matvec(da, dkt.Operator.dense(Kl, case["dim"] - 2.0, dirichlet=diri), u, n, rank, world, scale=0.7)
+                err = np.abs(v - want).max() / np.abs(want).max()
+                if rank == 0:
+                    print("%-24s ranks=%d laplacian dirichlet=%d rel err vs reference %.2e" % (name, world, diri, err))
+                ok &= err < 1e-12
         da.close()
     # (b) a larger tree against the single-GPU path
     dim, md = 4, 10

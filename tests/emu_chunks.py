@@ -38,7 +38,7 @@ def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None,
     families (families=0 builds per-element sets only, DKT_FAMILIES=0).
     phased_seed: emulate a partitioned DA with comm/compute overlap - a random third of the elements counts as
     "boundary", the lists are ordered [interior | boundary] like dkt_dist.cu does, visit positions get an offset,
-    and the three phases run one after the other."""
+    and the phases (interior, boundary) run one after the other."""
     import flat
     dim, N = t.dim, t.N
     nMv = len(t.mv_lev)

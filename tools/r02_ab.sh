@@ -10,6 +10,6 @@ for v in "$@"; do
 done
 if [ -n "$NCU_VARIANT" ] || [ -n "$NCU" ]; then
   L=$PWD/dendro-kt_b200/lib/libdkt${NCU_VARIANT:+_$NCU_VARIANT}.so
-  DKT_LIB=$L timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mvf -s 2 -c 1 -f -o $O/prof_mvf \
+  DKT_LIB=$L timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mvf -s 6 -c 1 -f -o $O/prof_mvf \
     python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $O/ncu_full.log 2>&1
 fi
