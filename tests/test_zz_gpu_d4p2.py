@@ -1,6 +1,6 @@
 """GPU parity of 4-D order 2 (81 nodes per element: generic table construction + the loop-based flat kernels k_mv_big
-of dkt_matvec.cu).  The same assertions run on the CPU under the emulation (tests/test_emu_full.py); this file is
-opt-in (DKT_TEST_D4P2=1, tools/r02_gpu1.sh) until the kernels have been confirmed on a B200."""
+of dkt_matvec.cu).  The same assertions run on the CPU under the emulation (tests/test_emu_full.py).  Confirmed on a B200 in
+round 2 (gpurun_out/r02_optin/d4p2.log: 2 passed)."""
 import os
 
 import numpy as np
@@ -9,7 +9,7 @@ import pytest
 import cases
 from test_oracle import load_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("DKT_TEST_D4P2") != "1", reason="opt-in: DKT_TEST_D4P2=1")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 

@@ -1,7 +1,10 @@
 """The peer-memory ghost exchange (DKT_DIST_P2P, dendro-kt_b200/csrc/dkt_dist.cu: k_p2p_*) on ONE GPU: the dry-run
 DAs of all ranks of a partition live in this process, dkt_p2p_attach_local wires their exchange buffers directly, and
 the ranks' matvecs run concurrently on their own streams - same kernels, flags and protocol as between processes,
-without IPC and NCCL.  Opt-in (DKT_TEST_P2P=1, tools/r02_gpu1.sh) until the path has been confirmed on a B200."""
+without IPC and NCCL.  Opt-in (DKT_TEST_P2P=1) and for small partitions only: on ONE GPU the spinning wait kernels of one rank
+can fill the device before the other rank's put kernels are resident (round 2: the level-5 tree deadlocks and the 30 s
+time-out traps), which cannot happen between GPUs.  The protocol between processes is covered by tests/test_gpu_dist.py
+(torchrun, DKT_DIST_P2P=1), green on 2 B200s."""
 import os
 
 import numpy as np
