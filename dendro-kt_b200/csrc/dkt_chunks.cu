@@ -147,7 +147,7 @@ __global__ void k_unit_slots_elem(const uint32_t *e2n, const uint32_t *pnode, co
 template <bool WRITE, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, const uint32_t *refcnt, const uint8_t *isbdy,
-              const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out, uint32_t *slot, uint16_t *rk16,
+              const uint8_t *sent, const uint64_t *node_off, int jdStride, uint32_t *nloc_out, uint32_t *maxlen_out, uint32_t *slot, uint16_t *rk16,
               uint16_t *inv16, uint32_t *gid_out, uint16_t *meta_out, uint32_t *rec_out, uint16_t *jd_out)
 {
   constexpr int CAP = SORT_THREADS * ITEMS;
@@ -394,7 +394,7 @@ k_chunk_build(const uint32_t *U, uint64_t nUnits, int spu, int upc, int fam, con
       const int n0 = rank0[i];
       const int len = (int)s_cw[n0 + 1] - (int)s_cw[n0];
       uint32_t m = (uint32_t)len | META_PRESENT;
-      if (refcnt[key[i]] != (uint32_t)len) m |= META_SHARED;
+      if (refcnt[key[i]] != (uint32_t)len || (sent && sent[key[i]])) m |= META_SHARED;
       if (isbdy[key[i]]) m |= META_BDY;
       if (!fam)
       {
@@ -443,7 +443,7 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
   CK(cudaMalloc((void **)&off, ((size_t)cs.nChunks + 1) * sizeof(uint64_t)));
   auto kcount = k_chunk_build<false, SORT_ITEMS>;
   auto kwrite = k_chunk_build<true, SORT_ITEMS>;
-  DKT_LAUNCH(kcount, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, nullptr, 0, nloc, mlen,
+  DKT_LAUNCH(kcount, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, da.d_node_sent, nullptr, 0, nloc, mlen,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   g_launches++;
   CK(cudaMemsetAsync(wide, 0, ((size_t)cs.nChunks + 1) * sizeof(uint64_t), da.stream));
@@ -490,7 +490,7 @@ static int build_set(DA &da, ChunkSet &cs, const uint32_t *U, const uint32_t *re
     cs.d_nloc = nloc;
   }
   CK(cudaMalloc((void **)&cs.d_jd, (size_t)cs.nChunks * cs.jdStride * (fam ? 2 : 1) * sizeof(uint16_t)));
-  DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, off, (int)cs.jdStride, nullptr,
+  DKT_LAUNCH(kwrite, cs.nChunks, SORT_THREADS, 0, da.stream)(U, nSet, spu, upc, fam, refcnt, da.d_node_isbdy, da.d_node_sent, off, (int)cs.jdStride, nullptr,
                                                               nullptr, cs.d_slot, cs.d_rk16, cs.d_inv16, cs.d_gid, cs.d_meta, (uint32_t *)cs.d_rec,
                                                               cs.d_jd);
   g_launches++;

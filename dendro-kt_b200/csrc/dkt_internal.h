@@ -82,6 +82,9 @@ struct DA
   uint8_t *d_node_lev = nullptr;
   uint32_t *d_bdy = nullptr;       // [nBdy]
   uint8_t *d_node_isbdy = nullptr; // [nNodes]
+  // partitioned DA: [nNodes] 1 = owned node that other ranks ghost.  Its chunk entries are accumulated with RED even when a
+  // single chunk touches it, so that the returned partial sums may be added while the elements still run (dkt_dist.cu)
+  uint8_t *d_node_sent = nullptr;
 
   // visited elements: regular ones first [0,nReg), hanging ones after [nReg,nMv)
   uint32_t *d_e2n = nullptr;       // [nMv*N]

@@ -67,6 +67,12 @@ __device__ __forceinline__ void p2p_wait(const volatile uint32_t *flags, const u
   }
   __syncthreads();
 }
+// ONE block that waits: launched in front of the kernels below, so that their many blocks find the flags raised and never sit
+// spinning on the SMs beside the element kernels
+static __global__ void k_p2p_gate(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, int *err)
+{
+  p2p_wait(flags, seg_off, nranks, epoch, err);
+}
 static __global__ void k_p2p_wait_copy(const volatile uint32_t *flags, const uint64_t *seg_off, int nranks, uint32_t epoch, const double *x,
                                 double *dst, uint64_t n, int *err)
 {
