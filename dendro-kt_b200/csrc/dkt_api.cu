@@ -290,6 +290,23 @@ extern "C"
     return DKT_OK;
   }
 
+  // ---- ghost exchanges of ot::DA (include/oda.h:300-322) on a device vector in the ghosted layout ---------------------------
+  static int ghost_begin(dkt_da *da, double *vec, int which)
+  {
+    if (!da || !vec) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    CKA(cudaSetDevice(da->d.device));
+    if (!da->dist.active) return DKT_OK;  // single rank: nothing to exchange (include/oda.tcc:216,324)
+    return ghost_exchange_begin(da->d, da->dist, vec, which);
+  }
+  int dkt_ghost_read_begin(dkt_da *da, double *vec) { return ghost_begin(da, vec, 0); }
+  int dkt_ghost_write_begin(dkt_da *da, double *vec) { return ghost_begin(da, vec, 1); }
+  int dkt_ghost_read_end(dkt_da *da, double *vec)
+  {
+    if (!da || !vec) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    return da->dist.active ? ghost_exchange_end(da->d, da->dist) : DKT_OK;
+  }
+  int dkt_ghost_write_end(dkt_da *da, double *vec) { return dkt_ghost_read_end(da, vec); }
+
   int dkt_cg_solve(dkt_da *da, const dkt_op *op, double *x, const double *b, int max_iter, double *tol, double scale,
                    unsigned flags, int *iters, int *status)
   {

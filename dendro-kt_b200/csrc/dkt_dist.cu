@@ -792,6 +792,48 @@ static int run_matvec_dist_p2p(DA &da, Dist &d, const dkt_op *op, const double *
   return DKT_OK;
 }
 
+// The ghost exchanges of ot::DA on their own (include/oda.tcc:212-435), on a DEVICE vector in the ghosted layout
+// [owned | ghosts grouped by owner].  begin: the exchange is queued on the exchange stream behind the work already queued on the
+// DA's stream; end: the DA's stream waits for it.  read: owners -> ghosts.  write: ghost entries -> owners, ACCUMULATED into the
+// owned entries (the reference's writeToGhostsEnd adds, oda.tcc:420-431).  which: 0 read, 1 write.
+int ghost_exchange_begin(DA &da, Dist &d, double *vec, int which)
+{
+  if (d.nranks <= 1) return DKT_OK;
+  if (!d.comm) { set_error("ghost exchange: no communicator (dry-run partition)"); return DKT_ERR_INVALID; }
+  cudaStream_t s = da.stream, cs = d.comm_stream;
+  const uint64_t nOwned = d.nOwned, totalSend = d.send_off[d.nranks];
+  CK(cudaEventRecord(d.ev[0], s));
+  CK(cudaStreamWaitEvent(cs, d.ev[0], 0));
+  if (which == 0) LAUNCHS(k_pack, totalSend, cs, vec, d.d_send_idx, totalSend, d.d_send_buf);
+  NCK(g_nccl.GroupStart());
+  for (int p = 0; p < d.nranks; p++)
+  {
+    if (p == d.rank) continue;
+    const uint64_t sc = d.send_off[p + 1] - d.send_off[p], rcv = d.recv_off[p + 1] - d.recv_off[p];
+    if (which == 0)
+    {
+      if (sc) NCK(g_nccl.Send(d.d_send_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+      if (rcv) NCK(g_nccl.Recv(vec + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+    }
+    else
+    {
+      if (rcv) NCK(g_nccl.Send(vec + nOwned + d.recv_off[p], rcv, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+      if (sc) NCK(g_nccl.Recv(d.d_recv_buf + d.send_off[p], sc, NCCL_FLOAT64, p, (ncclComm_p)d.comm, cs));
+    }
+  }
+  NCK(g_nccl.GroupEnd());
+  g_launches++;
+  if (which == 1) LAUNCHS(k_unpack_add, totalSend, cs, vec, d.d_send_idx, totalSend, d.d_recv_buf);
+  CK(cudaEventRecord(d.ev[1], cs));
+  return DKT_OK;
+}
+int ghost_exchange_end(DA &da, Dist &d)
+{
+  if (d.nranks <= 1) return DKT_OK;
+  CK(cudaStreamWaitEvent(da.stream, d.ev[1], 0));
+  return DKT_OK;
+}
+
 // v = A u on the partition: in/out are DEVICE vectors of the nOwned owned nodes
 int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
 {

@@ -163,6 +163,8 @@ int run_matvec_dist(DA &da, Dist &d, const dkt_op *op, const double *d_in, doubl
 // the same in stages (bit mask, see run_matvec_dist_p2p): only for the single-process emulation of several ranks
 int run_matvec_dist_stages(DA &da, Dist &d, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags,
                            unsigned stages);
+int ghost_exchange_begin(DA &da, Dist &d, double *vec, int which);  // which: 0 read (owners -> ghosts), 1 write (ghosts -> owners, added)
+int ghost_exchange_end(DA &da, Dist &d);
 void free_dist(Dist &d);
 int nccl_unique_id(void *out128);
 int p2p_attach_local(Dist **ranks, int R);

@@ -3,24 +3,29 @@
 #define DKT_HOST_FEMAT_H
 
 #include "oda.h"
+#include "point.h"
 
 template <unsigned int dim>
 class feMat
 {
 protected:
-  ot::DA<dim> *m_uiOctDA;  // not owned (feMat.h:45-50)
-  double m_uiPtMin[dim], m_uiPtMax[dim];
+  static constexpr unsigned int m_uiDim = dim;
+  ot::DA<dim> *m_uiOctDA;            // not owned (feMat.h:45-50)
+  Point<dim> m_uiPtMin, m_uiPtMax;   // problem domain (feMat.h:33-37); the unit cube unless set
 
 public:
-  feMat(ot::DA<dim> *da) : m_uiOctDA(da)
-  {
-    for (unsigned d = 0; d < dim; d++) { m_uiPtMin[d] = 0.0; m_uiPtMax[d] = 1.0; }
-  }
+  feMat(ot::DA<dim> *da) : m_uiOctDA(da), m_uiPtMin(0.0), m_uiPtMax(1.0) {}
   virtual ~feMat() {}
   virtual void matVec(const VECType *in, VECType *out, double scale = 1.0) = 0;
+  inline void setProblemDimensions(const Point<dim> &pt_min, const Point<dim> &pt_max)
+  {
+    m_uiPtMin = pt_min;
+    m_uiPtMax = pt_max;
+  }
   void setProblemDimensions(const double *pt_min, const double *pt_max)
   {
-    for (unsigned d = 0; d < dim; d++) { m_uiPtMin[d] = pt_min[d]; m_uiPtMax[d] = pt_max[d]; }
+    m_uiPtMin = Point<dim>(pt_min);
+    m_uiPtMax = Point<dim>(pt_max);
   }
 };
 #endif

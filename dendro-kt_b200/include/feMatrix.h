@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "feMat.h"
+#include "refel.h"
+#include "tensor.h"
 
 template <typename LeafT, unsigned int dim>
 class feMatrix : public feMat<dim>

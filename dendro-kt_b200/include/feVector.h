@@ -5,9 +5,10 @@
 #define DKT_HOST_FEVECTOR_H
 
 #include "feMatrix.h"
+#include "feVec.h"
 
 template <typename LeafT, unsigned int dim>
-class feVector
+class feVector : public feVec<dim>
 {
   // adaptor: expose elementalComputeVec as an elementalMatVec
   struct Adaptor : public feMatrix<Adaptor, dim>
@@ -24,11 +25,11 @@ class feVector
   Adaptor m_impl;
 
 protected:
-  ot::DA<dim> *m_uiOctDA;
+  using feVec<dim>::m_uiOctDA;
   unsigned int m_uiDof;
 
 public:
-  feVector(ot::DA<dim> *da, unsigned int dof = 1) : m_impl(da, this), m_uiOctDA(da), m_uiDof(dof) {}
+  feVector(ot::DA<dim> *da, unsigned int dof = 1) : feVec<dim>(da), m_impl(da, this), m_uiDof(dof) {}
   virtual ~feVector() {}
   virtual void elementalComputeVec(const VECType *in, VECType *out, double *coords, double scale) = 0;
   LeafT &asLeaf() { return static_cast<LeafT &>(*this); }

@@ -4,10 +4,16 @@
 #ifndef DKT_HOST_ODA_H
 #define DKT_HOST_ODA_H
 
+#include <algorithm>
 #include <cstring>
+#include <functional>
+#include <iostream>
+#include <type_traits>
 #include <vector>
 
 #include "treeNode.h"
+#include "mathUtils.h"
+#include "refel.h"
 
 namespace ot
 {
@@ -25,26 +31,60 @@ class DA
   TreeNode<C, dim> m_treePartFront, m_treePartBack;
   std::vector<unsigned int> m_uiBdyNodeIds;
   dkt_sizes m_sizes;
+  RefElement m_refel;  // include/oda.h:137
 
   DA(const DA &) = delete;
   DA &operator=(const DA &) = delete;
 
 public:
-  DA() { std::memset(&m_sizes, 0, sizeof(m_sizes)); }
+  DA() : m_refel(dim, 1) { std::memset(&m_sizes, 0, sizeof(m_sizes)); }
 
   /** @param inTree 2:1 balanced, complete linear tree (sorted or not: the SFC sort runs on the GPU)
    *  @param sfcMode DKT_SFC_MORTON (the reference's default build) or DKT_SFC_HILBERT
    *  @param ip0,ip1 RefElement::getIMChild0/1() of the host's reference element, or null */
   DA(const TreeNode<C, dim> *inTree, unsigned int nEle, MPI_Comm comm, unsigned int order, unsigned int grainSz = 100,
      double sfc_tol = 0.3, int sfcMode = DKT_SFC_MORTON, const double *ip0 = nullptr, const double *ip1 = nullptr)
+      : m_refel(dim, order)
   {
     (void)grainSz; (void)sfc_tol;
     construct(inTree, nEle, comm, order, sfcMode, ip0, ip1);
   }
   DA(const DistTree<C, dim> &tree, MPI_Comm comm, unsigned int order, unsigned int grainSz = 100, double sfc_tol = 0.3)
+      : m_refel(dim, order)
   {
     (void)grainSz; (void)sfc_tol;
     construct(tree.getTreePartFiltered().data(), (unsigned)tree.size(), comm, order, DKT_SFC_MORTON, nullptr, nullptr);
+  }
+  /** Regular grid (include/oda.h:155, include/oda.tcc:15-62): the uniform tree of the smallest level with at least
+   *  nProc * grainSz elements, 2^(dim * level) of them; one process drives one GPU here, so nProc = 1. */
+  DA(MPI_Comm comm, unsigned int order, unsigned int grainSz = 100, double sfc_tol = 0.3) : m_refel(dim, order)
+  {
+    (void)sfc_tol;
+    if (grainSz == 0) grainSz = 1;
+    unsigned int bits = 0;
+    for (unsigned int v = grainSz - 1; v; v >>= 1) bits++;        // binOp::binLength(nProc * grainSz - 1)
+    const unsigned int endL = (bits + dim - 1) / dim;
+    if (endL > m_uiMaxDepth) throw std::runtime_error("regular grid deeper than m_uiMaxDepth");
+    const unsigned int n1 = 1u << endL, len = 1u << (m_uiMaxDepth - endL);
+    size_t n = 1;
+    for (unsigned d = 0; d < dim; d++) n *= n1;
+    std::vector<TreeNode<C, dim>> tree(n);
+    for (size_t i = 0; i < n; i++)
+    {
+      std::array<C, dim> c;
+      size_t r = i;
+      for (unsigned d = 0; d < dim; d++) { c[d] = (C)(r % n1) * len; r /= n1; }
+      tree[i] = TreeNode<C, dim>(1, c, endL);
+    }
+    construct(tree.data(), (unsigned)n, comm, order);
+  }
+  /** The function-driven constructor of the reference (include/oda.h:167: refinement by interpolation error, then 2:1
+   *  balancing) belongs to the tree pipeline, which is outside this path: build the tree with the reference's
+   *  function2Octree / distTreeBalancing and pass it to the constructor above. */
+  template <typename T>
+  DA(std::function<void(const T *, T *)>, unsigned int, MPI_Comm, unsigned int, double, unsigned int = 100, double = 0.3) : m_refel(dim, 1)
+  {
+    throw std::runtime_error("ot::DA(function): tree generation is not part of the B200 matvec path; construct the DA from a tree");
   }
   ~DA() { if (m_handle) dkt_da_destroy(m_handle); }
 
@@ -53,6 +93,7 @@ public:
   {
     m_uiGlobalComm = comm;
     m_uiElementOrder = order;
+    if (!ip0 || !ip1) { ip0 = m_refel.getIMChild0(); ip1 = m_refel.getIMChild1(); }  // the reference uploads its own RefElement's
     std::vector<uint32_t> xyz((size_t)nEle * dim);
     std::vector<uint8_t> lev(nEle);
     for (unsigned i = 0; i < nEle; i++)
@@ -114,6 +155,7 @@ public:
   const TreeNode<C, dim> *getTreePartFront() const { return &m_treePartFront; }
   const TreeNode<C, dim> *getTreePartBack() const { return &m_treePartBack; }
   void getBoundaryNodeIndices(std::vector<unsigned int> &bdyIndex) const { bdyIndex = m_uiBdyNodeIds; }
+  const RefElement *getReferenceElement() const { return &m_refel; }  // include/oda.h:261
   /** the device-side object and its tree class: not part of the reference API */
   dkt_da *handle() const { return m_handle; }
   const dkt_sizes &sizes() const { return m_sizes; }
@@ -151,11 +193,25 @@ public:
     if (!isAllocated) createVector(local, false, false, dof);
     std::memcpy(local, gVec + (size_t)dof * m_uiLocalNodeBegin, sizeof(T) * dof * m_uiLocalNodalSz);
   }
-  // single rank: the exchanges are no-ops exactly as in the reference (include/oda.tcc:216,283,324,387)
-  template <typename T> void readFromGhostBegin(T *, unsigned int = 1) {}
-  template <typename T> void readFromGhostEnd(T *, unsigned int = 1) {}
-  template <typename T> void writeToGhostsBegin(T *, unsigned int = 1) {}
-  template <typename T> void writeToGhostsEnd(T *, unsigned int = 1) {}
+  // Ghost exchanges (include/oda.h:300-322).  One process drives one GPU: a DA made by these constructors is a single-rank DA and
+  // the exchanges are no-ops exactly as in the reference at one rank (include/oda.tcc:216,283,324,387).  For a partitioned DA
+  // (dkt_da_create_dist) the C ABI carries them: dkt_ghost_read_begin/end, dkt_ghost_write_begin/end on device vectors.
+  template <typename T> void readFromGhostBegin(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 0, true); }
+  template <typename T> void readFromGhostEnd(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 0, false); }
+  template <typename T> void writeToGhostsBegin(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 1, true); }
+  template <typename T> void writeToGhostsEnd(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 1, false); }
+
+private:
+  template <typename T>
+  void ghostOp(T *vec, unsigned int dof, int which, bool begin)
+  {
+    if (m_sizes.n_ranks <= 1) return;
+    if (dof != 1 || !std::is_same<T, double>::value) throw std::runtime_error("ghost exchange: dof == 1, double vectors");
+    double *v = reinterpret_cast<double *>(vec);
+    const int rc = which == 0 ? (begin ? dkt_ghost_read_begin(m_handle, v) : dkt_ghost_read_end(m_handle, v))
+                              : (begin ? dkt_ghost_write_begin(m_handle, v) : dkt_ghost_write_end(m_handle, v));
+    dkt_host::check(rc, "ghost exchange");
+  }
 };
 } // namespace ot
 #endif

@@ -172,6 +172,16 @@ void *dkt_da_stream(dkt_da *da);
 /* Launch on the caller's stream from now on (e.g. torch's current stream); NULL restores the
  * DA's own stream.  The caller keeps the stream alive. */
 int dkt_da_set_stream(dkt_da *da, void *cuda_stream);
+/* The ghost exchanges of ot::DA on their own - readFromGhostBegin/End, writeToGhostsBegin/End (reference include/oda.h:300-322,
+ * include/oda.tcc:212-435) - on a DEVICE vector of n_nodes + n_ghost_nodes doubles in the ghosted layout [owned | ghosts].
+ * begin queues the NCCL exchange on the DA's exchange stream behind the work already queued on its stream, end makes the
+ * stream wait for it (asynchronous with respect to the host).  read: owners -> ghost copies.  write: ghost entries -> their
+ * owners, ADDED to the owned entries.  No-ops on an unpartitioned DA, like the reference at one rank.  dkt_matvec performs
+ * both exchanges itself; these entry points serve callers that assemble or post-process ghosted vectors on their own. */
+int dkt_ghost_read_begin(dkt_da *da, double *vec);
+int dkt_ghost_read_end(dkt_da *da, double *vec);
+int dkt_ghost_write_begin(dkt_da *da, double *vec);
+int dkt_ghost_write_end(dkt_da *da, double *vec);
 /* Diagnostics of the chunked tables: out[0..4] = regular per-element sets {chunks, units per chunk, max nodes per
  * chunk, max run length, total chunk nodes}, out[5..9] = the same for the hanging per-element sets, out[10..14] for
  * the sibling-family sets (unit = family), out[15] = elements inside sibling families. */

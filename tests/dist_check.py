@@ -97,6 +97,31 @@ def main():
     if rank == 0:
         print("4-D ball level 6: %d elements, %d nodes, ranks=%d: rel diff vs single GPU %.2e" % (da1.n_elem, n, world, err))
     ok &= err < 1e-12
+    # (c) the ghost exchanges on their own (dkt_ghost_read/write): ghost copies equal the owners' values; a write-back of ones
+    # adds, to every owned node, the number of ranks that ghost it
+    ids = torch.from_numpy(daN.owned_ids().astype(np.int64)).cuda()
+    w = torch.zeros(daN.n_nodes + daN.n_ghost_nodes, dtype=torch.float64, device="cuda")
+    w[:daN.n_nodes] = ids.to(torch.float64)
+    torch.cuda.synchronize()  # the DA works on its own stream
+    daN.ghost_read(w)
+    torch.cuda.synchronize()
+    full = torch.zeros(n, dtype=torch.float64, device="cuda")
+    full[ids] = 1.0
+    dist.all_reduce(full)
+    gids = w[daN.n_nodes:].to(torch.int64)
+    okc = bool(((gids >= 0) & (gids < n)).all()) and bool((full[gids] == 1.0).all()) and not bool(torch.isin(gids, ids).any())
+    w2 = torch.ones_like(w)
+    torch.cuda.synchronize()
+    daN.ghost_write(w2)
+    torch.cuda.synchronize()
+    cnt = torch.zeros(n, dtype=torch.float64, device="cuda")
+    cnt[gids] += 0.0
+    cnt.index_add_(0, gids, torch.ones_like(gids, dtype=torch.float64))
+    dist.all_reduce(cnt)
+    okc &= bool((w2[:daN.n_nodes] == 1.0 + cnt[ids]).all())
+    if rank == 0:
+        print("ghost read/write entry points:", "ok" if okc else "MISMATCH")
+    ok &= okc
     daN.close()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
