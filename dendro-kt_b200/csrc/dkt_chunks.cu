@@ -1124,6 +1124,8 @@ struct Mv3Params
   double ip[2][M * M];
   double ipx[2][M * M];  // ip[0] and J ip[1] J (XOR-permuted coordinates)
   double K[N * N];
+  double kron[DKT_KRON_MAX_TERMS][DIM][M * M];  // DKT_OP_KRON: the 1-D factors
+  int nterms;
 };
 
 template <int DIM, int M, int AXIS, bool TRANSPOSE>
@@ -1217,6 +1219,7 @@ template <int DIM, int ORDER, int OPKIND>
 __device__ __forceinline__ void apply_op3(const Mv3Params<DIM, ORDER> &p, int lev, double *ein, double *eout)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
+  constexpr int M = ORDER + 1;
   if (OPKIND == DKT_OP_IDENTITY)
   {
 #pragma unroll
@@ -1229,6 +1232,45 @@ __device__ __forceinline__ void apply_op3(const Mv3Params<DIM, ORDER> &p, int le
 #pragma unroll
     for (int i = 0; i < N; i++) eout[i] = ein[i] * (p.K[i] * s);
     wht<N>(eout);
+  }
+  else if (OPKIND == DKT_OP_KRON)
+  {
+    // sum-factorised: every term is DIM axis passes with an M x M matrix (3-FMA dependency chains, no N x N table)
+    const double s = p.lscale[lev];
+#pragma unroll
+    for (int i = 0; i < N; i++) eout[i] = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < p.nterms; t++)
+    {
+      double tmp[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) tmp[i] = ein[i];
+      {
+        double A[M * M];
+#pragma unroll
+        for (int i = 0; i < M * M; i++) A[i] = p.kron[t][0][i];
+        axis_pass3<DIM, M, 0, false>(A, tmp);
+#pragma unroll
+        for (int i = 0; i < M * M; i++) A[i] = p.kron[t][1][i];
+        axis_pass3<DIM, M, 1, false>(A, tmp);
+        if (DIM >= 3)
+        {
+#pragma unroll
+          for (int i = 0; i < M * M; i++) A[i] = p.kron[t][DIM >= 3 ? 2 : 0][i];
+          axis_pass3<DIM, M, (DIM >= 3 ? 2 : 0), false>(A, tmp);
+        }
+        if (DIM >= 4)
+        {
+#pragma unroll
+          for (int i = 0; i < M * M; i++) A[i] = p.kron[t][DIM >= 4 ? 3 : 0][i];
+          axis_pass3<DIM, M, (DIM >= 4 ? 3 : 0), false>(A, tmp);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) eout[i] += tmp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) eout[i] *= s;
   }
   else
   {
@@ -1269,7 +1311,7 @@ __device__ __forceinline__ void xor_unpermute(T *v, int c)
 // the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
 // work in permuted coordinates throughout; the dense path un-permutes the slot words first.
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
-__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE) ? (HANG ? DKT_HANG_MINB : DKT_REG_MINB) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
+__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE && OPKIND != DKT_OP_KRON) ? (HANG ? DKT_HANG_MINB : DKT_REG_MINB) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
   constexpr int M = ORDER + 1;
@@ -1394,6 +1436,13 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
             wht<N>(ein);
 #pragma unroll
             for (int r = 0; r < N; r++) X[w[r] >> 16] = ein[r];
+          }
+          else if (OPKIND == DKT_OP_KRON)
+          {
+            double eout[N];
+            apply_op3<DIM, ORDER, OPKIND>(p, lev, ein, eout);
+#pragma unroll
+            for (int r = 0; r < N; r++) X[w[r] >> 16] = eout[r];
           }
           else
           {
@@ -1600,6 +1649,24 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
     p.exact_ip = dev <= 1e-13;
   }
   bool hadamard = false;
+  if (op->kind == DKT_OP_KRON)
+  {
+    if (!op->kref || op->terms < 1 || op->terms > DKT_KRON_MAX_TERMS) { set_error("DKT_OP_KRON needs 1..5 terms in kref"); return DKT_ERR_INVALID; }
+    if (ORDER == 1)
+    {
+      // order 1: the dense matrix is tiny and opens the Walsh-Hadamard form / the family kernel
+      static thread_local std::vector<double> Kd;
+      kron_to_dense(op, DIM, P::M, Kd);
+      dkt_op dense = *op;
+      dense.kind = DKT_OP_DENSE;
+      dense.kref = Kd.data();
+      return run_typed3<DIM, ORDER>(da, &dense, d_in, d_out, scale, flags, phaseMask, zeroOut);
+    }
+    p.nterms = op->terms;
+    for (int t = 0; t < op->terms; t++)
+      for (int d = 0; d < DIM; d++)
+        for (int i = 0; i < P::M * P::M; i++) p.kron[t][d][i] = op->kref[((size_t)(t * DIM + d)) * P::M * P::M + i];
+  }
   if (op->kind == DKT_OP_DENSE)
   {
     if (!op->kref) { set_error("DKT_OP_DENSE needs kref"); return DKT_ERR_INVALID; }
@@ -1657,6 +1724,11 @@ static int run_typed3(DA &da, const dkt_op *op, const double *d_in, double *d_ou
     return diri ? launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_IDENTITY, false>(da, *sets, p, phaseMask);
   if (op->kind == DKT_OP_DENSE)
     return diri ? launch_mv3<DIM, ORDER, DKT_OP_DENSE, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_DENSE, false>(da, *sets, p, phaseMask);
+  if constexpr (ORDER == 2)
+  {
+    if (op->kind == DKT_OP_KRON)
+      return diri ? launch_mv3<DIM, ORDER, DKT_OP_KRON, true>(da, *sets, p, phaseMask) : launch_mv3<DIM, ORDER, DKT_OP_KRON, false>(da, *sets, p, phaseMask);
+  }
   set_error("unknown operator kind");
   return DKT_ERR_INVALID;
 }

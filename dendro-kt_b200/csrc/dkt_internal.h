@@ -173,6 +173,8 @@ int dist_allreduce(Dist &d, double *red, cudaStream_t s);
 int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_b, int max_iter, double *tol, double scale,
              unsigned flags, int *iters, int *status);
 
+// DKT_OP_KRON -> the dense reference matrix it stands for (N x N row-major)
+void kron_to_dense(const dkt_op *op, int dim, int M, std::vector<double> &K);
 int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t n, unsigned flags);
 void free_da(DA &da);
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);

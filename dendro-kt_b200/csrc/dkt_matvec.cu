@@ -441,8 +441,35 @@ static int run_typed(DA &da, const dkt_op *op, const double *d_in, double *d_out
   return DKT_ERR_INVALID;
 }
 
+void kron_to_dense(const dkt_op *op, int dim, int M, std::vector<double> &K)
+{
+  int N = 1;
+  for (int d = 0; d < dim; d++) N *= M;
+  K.assign((size_t)N * N, 0.0);
+  for (int t = 0; t < op->terms; t++)
+    for (int i = 0; i < N; i++)      // output index
+      for (int j = 0; j < N; j++)    // input index
+      {
+        double v = 1.0;
+        for (int d = 0, ii = i, jj = j; d < dim; d++, ii /= M, jj /= M)
+          v *= op->kref[((size_t)(t * dim + d) * M + (jj % M)) * M + (ii % M)];  // A[k*M + j]: in k -> out j
+        K[(size_t)i * N + j] += v;
+      }
+}
+
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags)
 {
+  if (op->kind == DKT_OP_KRON)
+  {
+    // the flat kernels take the dense matrix the Kronecker terms stand for
+    if (!op->kref || op->terms < 1 || op->terms > DKT_KRON_MAX_TERMS) { set_error("DKT_OP_KRON needs 1..5 terms in kref"); return DKT_ERR_INVALID; }
+    static thread_local std::vector<double> K;
+    kron_to_dense(op, da.dim, da.order + 1, K);
+    dkt_op dense = *op;
+    dense.kind = DKT_OP_DENSE;
+    dense.kref = K.data();
+    return run_matvec(da, &dense, d_in, d_out, scale, flags);
+  }
   const int key = da.dim * 10 + da.order;
   switch (key)
   {

@@ -44,3 +44,15 @@ def mass_kref(dim, order):
     for _ in range(dim):
         T = np.kron(Mm, T)
     return T
+
+
+def laplace_terms(dim, order):
+    """The unit-cube stiffness matrix as a sum of `dim` Kronecker terms for dkt.Operator.kron: term a has the 1-D stiffness
+    matrix along axis a and the 1-D mass matrix along the others (what laplace_kref assembles densely).  Shape (dim, dim, M, M)."""
+    Mm, Km = _ref_1d(order)
+    return np.array([[Km if d == a else Mm for d in range(dim)] for a in range(dim)])
+
+
+def mass_terms(dim, order):
+    Mm, _ = _ref_1d(order)
+    return np.array([[Mm for _ in range(dim)]])

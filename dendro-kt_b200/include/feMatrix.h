@@ -63,6 +63,7 @@ public:
     op.kref = m_kref.data();
     op.alpha = m_alpha;
     op.dirichlet = 0;
+    op.terms = 0;
     dkt_host::check(dkt_matvec(da->handle(), &op, inG, outG, 1.0, DKT_VEC_HOST), "feMatrix::matVec");
     da->template ghostedNodalToNodalVec<VECType>(outG, out, true, m_uiDof);
     asLeaf().postMatVec(outG + da->getLocalNodeBegin(), out, scale);

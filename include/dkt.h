@@ -56,6 +56,9 @@ extern "C" {
 /* elemental operator kinds */
 #define DKT_OP_IDENTITY 0 /* out = in  (test/testMatvec.cpp:177-198)                        */
 #define DKT_OP_DENSE 1    /* out = scale * 2^(-alpha*level) * kref * in                     */
+#define DKT_OP_KRON 2     /* sum-factorised: out = scale * 2^(-alpha*level) * sum_t (A[t][dim-1] x .. x A[t][0]) in,
+                             the form of HeatMat / HeatVec (FEM/examples/src/heatMat.cpp:46-117, FEM/src/tensor.cpp:19-107) */
+#define DKT_KRON_MAX_TERMS 5
 
 typedef struct dkt_da dkt_da;
 
@@ -70,6 +73,10 @@ typedef struct dkt_op
   double alpha;        /* level exponent: K_e = scale * 2^(-alpha*L) * kref                 */
   int dirichlet;       /* 1: zero domain-boundary entries of input and output, like
                           HeatMat::preMatVec/postMatVec (FEM/examples/src/heatMat.cpp:120-139) */
+  int terms;           /* DKT_OP_KRON: number of Kronecker terms (<= DKT_KRON_MAX_TERMS); kref then holds terms * dim matrices of
+                          M x M doubles (M = order + 1), term-major, axis 0 first: A[t][d][k*M + j] takes input index k to output
+                          index j along axis d - the layout of the reference's 1-D operators (FEM/include/refel.h).  Order 2
+                          runs them as axis passes in registers; order 1 and the flat kernels expand them to kref.           */
 } dkt_op;
 
 typedef struct dkt_sizes

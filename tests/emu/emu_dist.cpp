@@ -44,7 +44,7 @@ extern "C" int emu_dist_matvec(int dim, int order, int max_depth, int sfc, const
     if (rc == DKT_OK) rc = build_chunks(da);
   }
   dkt_op op;
-  op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet; op.terms = 0;
   if (rc == DKT_OK && p2p)
   {
     // the library's own peer-memory flow (run_matvec_dist_p2p), stage by stage over all ranks, twice (buffer re-use)

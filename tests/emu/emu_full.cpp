@@ -59,7 +59,7 @@ extern "C" int emu_da_matvec(void *h, int kind, const double *kref, double alpha
 {
   DA &d = *(DA *)h;
   dkt_op op;
-  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet; op.terms = 0;
   double *din = nullptr, *dout = nullptr;
   cudaMalloc(&din, d.nNodes * sizeof(double));
   cudaMalloc(&dout, d.nNodes * sizeof(double));
@@ -78,7 +78,7 @@ extern "C" int emu_da_cg(void *h, int kind, const double *kref, double alpha, in
 {
   DA &d = *(DA *)h;
   dkt_op op;
-  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+  op.kind = kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet; op.terms = 0;
   double *dx = nullptr, *db = nullptr;
   cudaMalloc(&dx, d.nNodes * sizeof(double));
   cudaMalloc(&db, d.nNodes * sizeof(double));

@@ -54,7 +54,7 @@ extern "C" int emu_matvec(int dim, int order, int max_depth, uint64_t nMv, uint6
       o[7] = cs.totalNodes | ((uint64_t)cs.phase << 56);
     }
     dkt_op op;
-    op.kind = op_kind; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet;
+    op.kind = op_kind & 15; op.kref = kref; op.alpha = alpha; op.dirichlet = dirichlet; op.terms = op_kind >> 4;  // DKT_OP_KRON: terms in the high bits
     double *din = dup(in, nNodes), *dout = dup((const double *)nullptr, nNodes);
     if (!phased) rc = run_matvec_chunked(da, &op, din, dout, scale, flags);
     else  // the three phases of run_matvec_dist, without the exchanges

@@ -32,7 +32,7 @@ def _p(a):
 
 
 def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None, dirichlet=False, families=1, flags=0, order=0,
-           phased_seed=None):
+           phased_seed=None, kron=None):
     """Emulated dkt chunk path on the oracle's FlatTables `t`.  Returns (v, sets) where sets lists
     (kind, rows, slots per unit, units, chunks, units per chunk, max nodes per chunk, total chunk nodes, phase); kind 2 = sibling
     families (families=0 builds per-element sets only, DKT_FAMILIES=0).
@@ -69,6 +69,10 @@ def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None,
     ip0 = np.ascontiguousarray(np.asarray(ip0, dtype=np.float64).ravel())
     ip1 = np.ascontiguousarray(np.asarray(ip1, dtype=np.float64).ravel())
     kr = None if kref is None else np.ascontiguousarray(np.asarray(kref, dtype=np.float64).ravel())
+    op_kind = 0 if kr is None else 1
+    if kron is not None:  # sum-factorised operator: (terms, dim, M, M)
+        kr = np.ascontiguousarray(np.asarray(kron, dtype=np.float64).ravel())
+        op_kind = 2 | (len(kron) << 4)
     u = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
     out = np.full(nNodes, np.nan)
     info = np.zeros(128, dtype=np.uint64)
@@ -81,7 +85,7 @@ def matvec(t, u, max_depth, kref=None, alpha=0.0, scale=1.0, ip0=None, ip1=None,
         L.emu_set_order(C.c_int(order))
         rc = L.emu_matvec(C.c_int(dim), C.c_int(t.order), C.c_int(max_depth), C.c_uint64(nMv), C.c_uint64(nReg), C.c_uint64(nNodes),
                           _p(e2n), _p(pnode), _p(xyz), _p(lev), _p(src), _p(isbdy), _p(ip0), _p(ip1),
-                          C.c_int(0 if kr is None else 1), None if kr is None else _p(kr), C.c_double(alpha), C.c_int(int(dirichlet)),
+                          C.c_int(op_kind), None if kr is None else _p(kr), C.c_double(alpha), C.c_int(int(dirichlet)),
                           _p(u), _p(out), C.c_double(scale), C.c_uint(flags), _p(info),
                           C.c_int(phased), C.c_uint64(nRegInt), C.c_uint64(nHangInt), C.c_uint64(src0))
     finally:

@@ -138,3 +138,26 @@ def test_emulated_random_trees(seed):
         v, _ = emu_chunks.matvec(t, u, md, kref=K, alpha=dim - 2.0, scale=0.9, dirichlet=True, families=spec, order=int(rng.integers(0, 3)),
                                  phased_seed=(None if rng.random() < 0.5 else int(rng.integers(0, 100))))
         assert rel(v, ref) <= TOL, spec
+
+
+@pytest.mark.parametrize("name", ["ex1-d2-p2-morton-4", "ex3-d3-p2-morton-3", "gauss-d3-p2-morton", "ball-d3-p1-morton-6", "ex3-d4-p1-morton-3"])
+def test_emulated_sum_factorised_operator(name):
+    """DKT_OP_KRON (sum of Kronecker products of 1-D matrices, the form of HeatMat/HeatVec): axis passes in registers at order
+    2, expanded to the dense matrix (and from there to the Walsh-Hadamard form / family kernel) at order 1 - against the oracle
+    with the dense matrix the terms stand for"""
+    import dkt
+    case, g, t = _tables(name)
+    dim, order, md = case["dim"], case["order"], case["max_depth"]
+    n = len(g["node_lev"])
+    u = cases.input_vector(n)
+    terms = np.concatenate([dkt.operators.laplace_terms(dim, order), 0.3 * dkt.operators.mass_terms(dim, order)])
+    K = np.zeros(((order + 1) ** dim,) * 2)
+    for term in terms:
+        T = np.ones((1, 1))
+        for d in range(dim):
+            T = np.kron(term[d].T, T)  # A[k, j]: in k -> out j  => matrix entry [j, k]
+        K += T
+    for diri in (False, True):
+        ref = flat.matvec(t, u, Kref=K, alpha=1.25, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri)
+        v, _ = emu_chunks.matvec(t, u, md, kron=terms, alpha=1.25, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri, order=2)
+        assert rel(v, ref) <= TOL

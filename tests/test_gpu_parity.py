@@ -93,6 +93,31 @@ def test_structured_operator_fast_path(dkt, name):
     da.close()
 
 
+@pytest.mark.parametrize("name", ["ex3-d3-p2-morton-3", "gauss-d3-p2-morton", "ex1-d2-p2-morton-4", "ball-d4-p1-morton-5"])
+def test_sum_factorised_operator(dkt, name):
+    """DKT_OP_KRON - the sum-factorised form of HeatMat/HeatVec (FEM/examples/src/heatMat.cpp:46-117): Laplacian + mass as
+    Kronecker terms of 1-D matrices, axis passes in registers at order 2 - against the oracle with the dense matrix the terms
+    stand for, and against the dense device operator"""
+    case = load_case(name)
+    g = case["golden"]
+    dim, order = case["dim"], case["order"]
+    da = dkt.DA(case["xyz"], case["lev"], dim, order, case["max_depth"], ip0=g["ip0"], ip1=g["ip1"])
+    t = cases.oracle_tables_for(case)
+    u = cases.input_vector(da.n_nodes)
+    mt = dkt.operators.mass_terms(dim, order)
+    mt[0, 0] *= 0.3  # the factor of a term goes into ONE of its 1-D matrices
+    terms = np.concatenate([dkt.operators.laplace_terms(dim, order), mt])
+    K = dkt.operators.laplace_kref(dim, order) + 0.3 * dkt.operators.mass_kref(dim, order)
+    for diri in (False, True):
+        vo = flat.matvec(t, u, K, alpha=1.25, scale=0.7, ip0=g["ip0"], ip1=g["ip1"], dirichlet=diri)
+        v = da.matvec(dkt.Operator.kron(terms, 1.25, dirichlet=diri), u, scale=0.7)
+        vd = da.matvec(dkt.Operator.dense(K, 1.25, dirichlet=diri), u, scale=0.7)
+        vf = da.matvec(dkt.Operator.kron(terms, 1.25, dirichlet=diri), u, scale=0.7, flat=True)
+        for x in (v, vd, vf):
+            assert np.abs(x - vo).max() <= TOL * np.abs(vo).max()
+    da.close()
+
+
 @pytest.mark.parametrize("fixture", ["heatmat-d3-p1-ball", "heatmat-d3-p1-ex3"])
 def test_reference_heatmat_operator(dkt, fixture):
     """v = A u of the reference's own HeatEq::HeatMat<3> (stiffness operator + Dirichlet pre/postMatVec,
