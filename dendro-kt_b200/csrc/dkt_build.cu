@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 namespace dkt
 {
@@ -620,6 +621,11 @@ int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t
   SfcTables tab;
   make_sfc_tables(dim, da.sfc_mode, tab);
   if (tab.nrot > 192) { set_error("internal: too many SFC rotations"); return DKT_ERR_UNSUPPORTED; }
+  // c_rot_inv / c_htab are per-process __constant__ symbols read by the key kernels below: two host threads building
+  // DAs of different (dim, sfc_mode) must not interleave the upload and the kernels that read it.  Construction
+  // synchronises the device before it returns (the size download), so holding the lock to the end is enough.
+  static std::mutex sfc_tables_mutex;
+  std::lock_guard<std::mutex> sfc_tables_lock(sfc_tables_mutex);
   CK(cudaMemcpyToSymbol(c_rot_inv, tab.rot_inv.data(), tab.rot_inv.size()));
   CK(cudaMemcpyToSymbol(c_htab, tab.htab.data(), tab.htab.size()));
 

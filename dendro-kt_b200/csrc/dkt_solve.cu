@@ -129,8 +129,23 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
   const uint64_t n = part ? dist->nOwned : da.nNodes;
   cudaStream_t s = da.stream;
   double *work = nullptr, *red = nullptr;
+  // the chunk tables carry quirk Q1 statically: the conservative variant runs on the flat kernels (as in dkt_matvec)
+  if (flags & DKT_NO_Q1_MASK) flags |= DKT_MV_FLAT;
+  // CUDA failures below leave through `done` (buffers released)
+#define CKD(call)                                                                                                      \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e_ = (call);                                                                                           \
+    if (e_ != cudaSuccess)                                                                                             \
+    {                                                                                                                  \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                                                   \
+      rc = DKT_ERR_CUDA;                                                                                               \
+      goto done;                                                                                                       \
+    }                                                                                                                  \
+  } while (0)
+  int rc = DKT_OK;
   CK(cudaMalloc((void **)&work, std::max<uint64_t>(n, 1) * 4 * sizeof(double)));
-  CK(cudaMalloc((void **)&red, 4 * sizeof(double)));
+  if (cudaMalloc((void **)&red, 4 * sizeof(double)) != cudaSuccess) { cudaFree(work); set_error("cg_solve: out of device memory"); return DKT_ERR_CUDA; }
   double *p = work, *Ap = work + n, *r0 = work + 2 * n, *r1 = work + 3 * n;
   const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), gridN = (unsigned)((n + 255) / 256);
   double h[4];
@@ -144,11 +159,10 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
     if (rc == DKT_OK && cudaMemcpyAsync(h, red, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = DKT_ERR_CUDA;
     if (rc == DKT_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = DKT_ERR_CUDA;
   };
-  int rc = DKT_OK;
   *status = 1;
   *iters = 0;
   // normb, r0 = b - A x, p = r0
-  CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
+  CKD(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
   if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(nullptr, nullptr, nullptr, nullptr, d_b, n, red);
   rc = mv(d_x, Ap);
   if (rc) goto done;
@@ -159,7 +173,7 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
   {
     double normb = h[2];
     if (normb == 0.0) normb = 1.0;
-    CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
+    CKD(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
     if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(r0, r0, nullptr, nullptr, r0, n, red);  // red[0] = r0.r0, red[2] = |r0|
     g_launches++;
     reduce(rc);
@@ -170,13 +184,13 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
     {
       rc = mv(p, Ap);
       if (rc) goto done;
-      CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
+      CKD(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
       if (n) DKT_SOLVE_LAUNCH(k_reduce3, grid, s)(nullptr, nullptr, p, Ap, nullptr, n, red);  // red[1] = p.Ap
       g_launches++;
       reduce(rc);
       if (rc) goto done;
       const double alpha = rr / h[1];
-      CK(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
+      CKD(cudaMemsetAsync(red, 0, 4 * sizeof(double), s));
       if (n) DKT_SOLVE_LAUNCH(k_cg_step1, grid, s)(alpha, p, Ap, r0, n, d_x, r1, red);
       g_launches++;
       reduce(rc);
@@ -192,6 +206,7 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
     *tol = resid;
   }
 done:
+#undef CKD
   cudaStreamSynchronize(s);
   cudaFree(work);
   cudaFree(red);

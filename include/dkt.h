@@ -122,7 +122,8 @@ int dkt_da_destroy(dkt_da *da);
  * path: SFC-contiguous element ranges (SFC_Tree::distTreePartition, src/tsort.cpp:229-508), node
  * ownership, and the ghost exchange readFromGhostBegin/End + writeToGhostsBegin/End
  * (include/oda.tcc:212-435) as ncclSend/ncclRecv groups.  Every rank passes the SAME full tree;
- * rank r keeps elements [r*n/R, (r+1)*n/R) of the tree order.  nccl_id: 128 bytes from
+ * rank r keeps a contiguous range of the tree order, cut so that the per-rank work (elements weighted by their
+ * interpolation cost, hanging > regular) is balanced -- not the equal-count split.  nccl_id: 128 bytes from
  * dkt_nccl_unique_id() on rank 0, broadcast by the caller (MPI, torch.distributed, a file ...).
  * Vectors passed to dkt_matvec then hold this rank's OWNED nodes (dkt_sizes.n_nodes of them);
  * dkt_da_export_owned_ids gives their index in the single-rank DA order. */
