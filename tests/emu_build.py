@@ -6,7 +6,9 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 CSRC = os.path.join(ROOT, "dendro-kt_b200", "csrc")
-BUILD = os.path.join(EMU, "_build")
+# DKT_EMU_CFLAGS="-DDKT_FAM_ALIAS=1 ..." emulates a build variant (its objects live in a directory of their own)
+EXTRA = os.environ.get("DKT_EMU_CFLAGS", "").split()
+BUILD = os.path.join(EMU, "_build" + ("_" + "".join(ch if ch.isalnum() else "_" for ch in "".join(EXTRA)) if EXTRA else ""))
 LIB = os.path.join(BUILD, "libdkt_emu_all.so")
 SOURCES = [os.path.join(CSRC, f) for f in ("dkt_build.cu", "dkt_chunks.cu", "dkt_family.cu", "dkt_matvec.cu", "dkt_dist.cu", "dkt_solve.cu", "dkt_sfc.cpp")] + \
           [os.path.join(EMU, f) for f in ("cuda_emu.cpp", "emu_common.cpp", "emu_harness.cpp", "emu_full.cpp", "emu_dist.cpp", "emu_p2p.cpp")]
@@ -22,7 +24,7 @@ def build():
         obj = os.path.join(BUILD, os.path.basename(src).rsplit(".", 1)[0] + ".o")
         objs.append(obj)
         if not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
-            cmd = ["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-fPIC", "-x", "c++", "-c",
+            cmd = ["g++", "-std=c++17", "-O1", "-g", "-DDKT_EMU", *EXTRA, "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, "-fPIC", "-x", "c++", "-c",
                    src, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = []
