@@ -42,6 +42,10 @@ struct dkt_da
   DA d;
   Dist dist;
 };
+struct dkt_tree
+{
+  Tree t;
+};
 
 #define CKA(call)                                                                                 \
   do                                                                                              \
@@ -83,6 +87,62 @@ extern "C"
   {
     if (!out128) { set_error("NULL argument"); return DKT_ERR_INVALID; }
     return nccl_unique_id(out128);
+  }
+  int dkt_tree_from_points(int dim, int max_depth, int sfc_mode, const uint32_t *pts_xyz, uint64_t n_pts, uint64_t max_pts_per_region,
+                           int balance, unsigned flags, dkt_tree **out)
+  {
+    if (!out) { set_error("out is NULL"); return DKT_ERR_INVALID; }
+    *out = nullptr;
+    if (!pts_xyz) { set_error("pts_xyz is NULL"); return DKT_ERR_INVALID; }
+    if (sfc_mode != DKT_SFC_MORTON && sfc_mode != DKT_SFC_HILBERT) { set_error("bad sfc_mode"); return DKT_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+      set_error("no CUDA device: libdkt has no CPU path");
+      return DKT_ERR_CUDA;
+    }
+    dkt_tree *t = new (std::nothrow) dkt_tree;
+    if (!t) { set_error("out of host memory"); return DKT_ERR_INVALID; }
+    t->t.dim = dim; t->t.max_depth = max_depth; t->t.sfc_mode = sfc_mode;
+    cudaGetDevice(&t->t.device);
+    const int rc = build_tree(t->t, pts_xyz, n_pts, max_pts_per_region, balance != 0, flags);
+    if (rc != DKT_OK) { free_tree(t->t); delete t; return rc; }
+    *out = t;
+    return DKT_OK;
+  }
+  int dkt_tree_size(const dkt_tree *t, uint64_t *n_elem, int *finest_level)
+  {
+    if (!t || !n_elem) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    *n_elem = t->t.n;
+    if (finest_level) *finest_level = t->t.finest_level;
+    return DKT_OK;
+  }
+  int dkt_tree_export(const dkt_tree *t, uint32_t *elem_xyz, uint8_t *elem_lev, unsigned flags)
+  {
+    if (!t || !elem_xyz || !elem_lev) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    CKA(cudaSetDevice(t->t.device));
+    const cudaMemcpyKind kind = (flags & DKT_ELEMS_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (t->t.n)
+    {
+      CKA(cudaMemcpy(elem_xyz, t->t.d_xyz, t->t.n * t->t.dim * sizeof(uint32_t), kind));
+      CKA(cudaMemcpy(elem_lev, t->t.d_lev, t->t.n, kind));
+    }
+    return DKT_OK;
+  }
+  int dkt_tree_device_ptrs(const dkt_tree *t, const uint32_t **elem_xyz, const uint8_t **elem_lev)
+  {
+    if (!t || !elem_xyz || !elem_lev) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    *elem_xyz = t->t.d_xyz;
+    *elem_lev = t->t.d_lev;
+    return DKT_OK;
+  }
+  int dkt_tree_destroy(dkt_tree *t)
+  {
+    if (!t) return DKT_OK;
+    cudaSetDevice(t->t.device);
+    free_tree(t->t);
+    delete t;
+    return DKT_OK;
   }
   int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_t *elem_xyz, const uint8_t *elem_lev,
                     uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out)

@@ -176,6 +176,17 @@ int cg_solve(DA &da, Dist *dist, const dkt_op *op, double *d_x, const double *d_
 // DKT_OP_KRON -> the dense reference matrix it stands for (N x N row-major)
 void kron_to_dense(const dkt_op *op, int dim, int M, std::vector<double> &K);
 int build_da(DA &da, const uint32_t *elem_xyz, const uint8_t *elem_lev, uint64_t n, unsigned flags);
+
+// A linear tree built on the device from points (dkt_tree.cu): leaves in tree order.
+struct Tree
+{
+  int dim = 0, max_depth = 0, sfc_mode = 0, device = 0, finest_level = 0;
+  uint64_t n = 0;
+  uint32_t *d_xyz = nullptr;  // [n * dim] anchors
+  uint8_t *d_lev = nullptr;   // [n]
+};
+int build_tree(Tree &t, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool balance, unsigned flags);
+void free_tree(Tree &t);
 void free_da(DA &da);
 int run_matvec(DA &da, const dkt_op *op, const double *d_in, double *d_out, double scale, unsigned flags);
 int build_chunks(DA &da);

@@ -27,6 +27,7 @@ DECLARED_SYMBOLS = [
     "dkt_nccl_unique_id", "dkt_da_create_dist", "dkt_p2p_attach_local", "dkt_da_export_owned_ids", "dkt_da_export_exchange",
     "dkt_da_export_elements", "dkt_da_export_nodes", "dkt_da_export_boundary", "dkt_da_export_tables", "dkt_matvec",
     "dkt_cg_solve", "dkt_ghost_read_begin", "dkt_ghost_read_end", "dkt_ghost_write_begin", "dkt_ghost_write_end", "dkt_last_kernel_ms", "dkt_da_chunk_info", "dkt_da_stream", "dkt_da_set_stream", "dkt_kernel_launch_count",
+    "dkt_tree_from_points", "dkt_tree_size", "dkt_tree_export", "dkt_tree_device_ptrs", "dkt_tree_destroy",
 ]
 
 
@@ -78,6 +79,11 @@ def lib():
     L.dkt_da_stream.argtypes = [vp]
     L.dkt_da_set_stream.argtypes = [vp, vp]
     L.dkt_da_chunk_info.argtypes = [vp, vp]
+    L.dkt_tree_from_points.argtypes = [i32, i32, i32, vp, u64, u64, i32, u32, C.POINTER(vp)]
+    L.dkt_tree_size.argtypes = [vp, C.POINTER(u64), C.POINTER(i32)]
+    L.dkt_tree_export.argtypes = [vp, vp, vp, u32]
+    L.dkt_tree_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.dkt_tree_destroy.argtypes = [vp]
     for f in ("dkt_ghost_read_begin", "dkt_ghost_read_end", "dkt_ghost_write_begin", "dkt_ghost_write_end"):
         getattr(L, f).argtypes = [vp, vp]
     L.dkt_kernel_launch_count.restype = u64
@@ -150,6 +156,66 @@ class Operator:
 
     def _c(self):
         return _Op(self.kind, None if self.kref is None else self.kref.ctypes.data, self.alpha, int(self.dirichlet), self.terms)
+
+
+class Tree:
+    """A linear tree built on the GPU from points: SFC_Tree<T,dim>::distTreeBalancing (balance=True) or
+    distTreeConstruction (balance=False) of the reference on one rank (src/tsort.cpp:647-716, 862-877).
+
+    pts: (n, dim) integer coordinates in [0, 2^max_depth) - numpy array or CUDA torch tensor."""
+
+    def __init__(self, pts, dim, max_depth, max_pts=1, balance=True, sfc=SFC_MORTON):
+        L = lib()
+        self.dim, self.max_depth, self.sfc = dim, max_depth, sfc
+        flags = 0
+        if _is_cuda(pts):
+            import torch
+            pts = pts.to(torch.int32).contiguous() if pts.dtype not in (torch.int32, torch.uint32) else pts.contiguous()
+            n = int(pts.numel()) // dim
+            flags |= ELEMS_ON_DEVICE
+        else:
+            pts = np.ascontiguousarray(pts, dtype=np.uint32).reshape(-1, dim)
+            n = len(pts)
+        h = C.c_void_p()
+        _check(L.dkt_tree_from_points(dim, max_depth, sfc, _ptr(pts), n, int(max_pts), int(bool(balance)), flags, C.byref(h)))
+        self._h = h
+        ne, fl = C.c_uint64(), C.c_int()
+        _check(L.dkt_tree_size(self._h, C.byref(ne), C.byref(fl)))
+        self.n_elem, self.finest_level = int(ne.value), int(fl.value)
+
+    def __len__(self):
+        return self.n_elem
+
+    def export(self):
+        """(xyz, lev) numpy arrays of the leaves in tree order."""
+        xyz = np.zeros((self.n_elem, self.dim), dtype=np.uint32)
+        lev = np.zeros(self.n_elem, dtype=np.uint8)
+        _check(lib().dkt_tree_export(self._h, _ptr(xyz), _ptr(lev), 0))
+        return xyz, lev
+
+    def export_torch(self):
+        """(xyz int32, lev uint8) CUDA tensors (copies; usable after the tree is closed)."""
+        import torch
+        xyz = torch.empty((self.n_elem, self.dim), dtype=torch.int32, device="cuda")
+        lev = torch.empty(self.n_elem, dtype=torch.uint8, device="cuda")
+        _check(lib().dkt_tree_export(self._h, _ptr(xyz), _ptr(lev), ELEMS_ON_DEVICE))
+        return xyz, lev
+
+    def da(self, order=1, **kw):
+        """ot::DA over this tree, built from the device arrays without a host round trip."""
+        xyz, lev = self.export_torch()
+        return DA(xyz, lev, self.dim, order, self.max_depth, sfc=self.sfc, presorted=True, **kw)
+
+    def close(self):
+        if self._h:
+            lib().dkt_tree_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class DA:

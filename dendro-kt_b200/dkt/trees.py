@@ -115,3 +115,27 @@ def gaussian_points(dim, n, max_depth, seed=7, sigma=0.04, guard_level=None):
         gp = ((g + 0.5) / m * (1 << max_depth)).astype(np.uint32)
         pts = np.concatenate([pts, gp])
     return pts
+
+
+def guard_points(dim, guard_level, max_depth):
+    """Centres of all level-`guard_level` cells: a uniform guard so that every boundary-touching leaf has the same level."""
+    m = 1 << guard_level
+    g = np.stack(np.meshgrid(*([np.arange(m)] * dim), indexing="ij"), -1).reshape(-1, dim)
+    return ((g + 0.5) / m * (1 << max_depth)).astype(np.uint32)
+
+
+def shell_points(dim, n, max_depth, seed=1331, radius=0.125, guard_level=3):
+    """points on a sphere shell moving through time (after test/testMovingBall.cpp:122-175, moved off the
+    domain boundary), plus a level-`guard_level` guard.  4-D: (x, y, z, t); lower dim drops trailing space axes and keeps t."""
+    rng = np.random.default_rng(seed)
+    theta = rng.uniform(0.0, 2.0 * np.pi, n)
+    zu = rng.uniform(-1.0, 1.0, n)
+    tau = rng.uniform(0.0, 1.0, n)
+    r, h = np.sqrt(np.abs(zu)), np.sqrt(1.0 - np.abs(zu))
+    t = 0.25 + 0.5 * tau
+    sp = np.stack([0.375 + radius * r * np.cos(theta), 0.375 + 0.25 * t + radius * r * np.sin(theta), 0.375 + radius * np.sign(zu) * h], 1)
+    p = np.concatenate([sp[:, :dim - 1], t[:, None]], 1)
+    pts = (np.clip(p, 0.0, 1.0 - 1e-12) * (1 << max_depth)).astype(np.uint32)
+    if guard_level is not None:
+        pts = np.concatenate([pts, guard_points(dim, guard_level, max_depth)])
+    return pts

@@ -118,6 +118,22 @@ int dkt_da_create(int dim, int order, int max_depth, int sfc_mode, const uint32_
                   uint64_t n_elem, const double *ip0, const double *ip1, unsigned flags, dkt_da **out);
 int dkt_da_destroy(dkt_da *da);
 
+/* Trees from points on the GPU.  Replaces SFC_Tree<T,dim>::distTreeConstruction (balance == 0) and distTreeBalancing
+ * (balance != 0) of the reference on one rank (src/tsort.cpp:566-716, 775-877; include/tsort.h:228-304): pts_xyz holds
+ * n_pts points, dim integer coordinates each in [0, 2^max_depth) (what TreeNode(coords, m_uiMaxDepth) holds); a region
+ * is split while it contains more than max_pts_per_region points and is coarser than max_depth; balancing adds what
+ * propagateNeighbours + the second construction add.  The result is the reference's leaf set in the reference's tree
+ * order (sfc_mode), bit-exact.  flags: DKT_ELEMS_ON_DEVICE = pts_xyz (and the export targets) are device pointers.
+ * dkt_tree_device_ptrs + dkt_da_create(..., DKT_ELEMS_ON_DEVICE | DKT_ELEMS_PRESORTED) builds a DA without a host
+ * round trip.  Limits: dim * max_depth <= 56, fewer than 2^32 points and leaves. */
+typedef struct dkt_tree dkt_tree;
+int dkt_tree_from_points(int dim, int max_depth, int sfc_mode, const uint32_t *pts_xyz, uint64_t n_pts, uint64_t max_pts_per_region,
+                         int balance, unsigned flags, dkt_tree **out);
+int dkt_tree_size(const dkt_tree *t, uint64_t *n_elem, int *finest_level /* may be NULL */);
+int dkt_tree_export(const dkt_tree *t, uint32_t *elem_xyz, uint8_t *elem_lev, unsigned flags);
+int dkt_tree_device_ptrs(const dkt_tree *t, const uint32_t **elem_xyz, const uint8_t **elem_lev); /* owned by the tree */
+int dkt_tree_destroy(dkt_tree *t);
+
 /* Multi-GPU, one process per GPU.  Replaces the distributed DA of the reference for the matvec
  * path: SFC-contiguous element ranges (SFC_Tree::distTreePartition, src/tsort.cpp:229-508), node
  * ownership, and the ghost exchange readFromGhostBegin/End + writeToGhostsBegin/End

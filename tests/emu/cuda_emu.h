@@ -305,6 +305,17 @@ struct DeviceRadixSort
     for (int64_t i = 0; i < n; i++) { kout[i] = kk[i]; vout[i] = vv[i]; }
     return cudaSuccess;
   }
+  template <typename K>
+  static cudaError_t SortKeys(void *tmp, size_t &bytes, const K *kin, K *kout, int64_t n, int b0, int b1, cudaStream_t)
+  {
+    if (!tmp) { bytes = 16; return cudaSuccess; }
+    const int w = b1 - b0;
+    const uint64_t mask = w >= 64 ? ~0ull : ((1ull << w) - 1);
+    std::vector<K> kk(kin, kin + n);
+    std::stable_sort(kk.begin(), kk.end(), [&](K a, K b) { return (((uint64_t)a >> b0) & mask) < (((uint64_t)b >> b0) & mask); });
+    for (int64_t i = 0; i < n; i++) kout[i] = kk[i];
+    return cudaSuccess;
+  }
 };
 struct DeviceScan
 {

@@ -96,3 +96,31 @@ extern "C" void emu_da_destroy(void *h)
   free_da(*da);
   delete da;
 }
+
+// ---- dkt_tree.cu: trees from points -------------------------------------------------------------------------------------
+extern "C" void *emu_tree_from_points(int dim, int max_depth, int sfc, const uint32_t *pts, uint64_t n, uint64_t max_pts, int balance)
+{
+  Tree *t = new Tree;
+  t->dim = dim; t->max_depth = max_depth; t->sfc_mode = sfc;
+  if (build_tree(*t, pts, n, max_pts, balance != 0, 0) != DKT_OK)
+  {
+    const std::string keep = g_err;
+    free_tree(*t);
+    delete t;
+    g_err = keep;
+    return nullptr;
+  }
+  return t;
+}
+extern "C" uint64_t emu_tree_size(void *h) { return ((Tree *)h)->n; }
+extern "C" void emu_tree_export(void *h, uint32_t *xyz, uint8_t *lev)
+{
+  const Tree &t = *(Tree *)h;
+  cp(xyz, t.d_xyz, t.n * t.dim);
+  cp(lev, t.d_lev, t.n);
+}
+extern "C" void emu_tree_destroy(void *h)
+{
+  free_tree(*(Tree *)h);
+  delete (Tree *)h;
+}

@@ -10,7 +10,7 @@ CSRC = os.path.join(ROOT, "dendro-kt_b200", "csrc")
 EXTRA = os.environ.get("DKT_EMU_CFLAGS", "").split()
 BUILD = os.path.join(EMU, "_build" + ("_" + "".join(ch if ch.isalnum() else "_" for ch in "".join(EXTRA)) if EXTRA else ""))
 LIB = os.path.join(BUILD, "libdkt_emu_all.so")
-SOURCES = [os.path.join(CSRC, f) for f in ("dkt_build.cu", "dkt_chunks.cu", "dkt_family.cu", "dkt_matvec.cu", "dkt_dist.cu", "dkt_solve.cu", "dkt_sfc.cpp")] + \
+SOURCES = [os.path.join(CSRC, f) for f in ("dkt_build.cu", "dkt_chunks.cu", "dkt_family.cu", "dkt_matvec.cu", "dkt_dist.cu", "dkt_solve.cu", "dkt_tree.cu", "dkt_sfc.cpp")] + \
           [os.path.join(EMU, f) for f in ("cuda_emu.cpp", "emu_common.cpp", "emu_harness.cpp", "emu_full.cpp", "emu_dist.cpp", "emu_p2p.cpp")]
 HEADERS = [os.path.join(EMU, "cuda_emu.h"), os.path.join(CSRC, "dkt_internal.h"), os.path.join(CSRC, "dkt_chunks.h"), os.path.join(CSRC, "dkt_p2p.cuh"),
            os.path.join(ROOT, "include", "dkt.h")]

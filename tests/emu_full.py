@@ -30,6 +30,12 @@ def lib():
     L.emu_da_cg.restype = C.c_int
     L.emu_da_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double,
                             C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.emu_tree_from_points.restype = C.c_void_p
+    L.emu_tree_from_points.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+    L.emu_tree_size.restype = C.c_uint64
+    L.emu_tree_size.argtypes = [C.c_void_p]
+    L.emu_tree_export.argtypes = [C.c_void_p] * 3
+    L.emu_tree_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -104,3 +110,18 @@ class EmuDA:
         if self._h:
             lib().emu_da_destroy(self._h)
             self._h = None
+
+
+def tree_from_points(pts, dim, max_depth, max_pts=1, balance=True, sfc=0):
+    """dkt_tree.cu's build_tree, emulated: (xyz, lev) of the leaves in tree order."""
+    L = lib()
+    pts = np.ascontiguousarray(pts, dtype=np.uint32).reshape(-1, dim)
+    h = L.emu_tree_from_points(dim, max_depth, sfc, _p(pts), len(pts), max_pts, int(balance))
+    if not h:
+        raise RuntimeError("emu_tree_from_points: " + L.emu_last_error().decode())
+    n = L.emu_tree_size(h)
+    xyz = np.zeros((n, dim), dtype=np.uint32)
+    lev = np.zeros(n, dtype=np.uint8)
+    L.emu_tree_export(h, _p(xyz), _p(lev))
+    L.emu_tree_destroy(h)
+    return xyz, lev
