@@ -34,6 +34,9 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -353,6 +356,16 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
   if (n == 0) { set_error("dkt_tree_from_points: no points (the reference returns an empty tree)"); return DKT_ERR_INVALID; }
   if (n >= 0xFFFFFFFFull) { set_error("dkt_tree_from_points: too many points"); return DKT_ERR_UNSUPPORTED; }
   cudaStream_t stream = 0;
+  // DKT_TREE_TIMING=1: host-side stage times (diagnostics; adds a device synchronisation per stage)
+  const bool timing = getenv("DKT_TREE_TIMING") && atoi(getenv("DKT_TREE_TIMING"));
+  auto tprev = std::chrono::steady_clock::now();
+  auto stage = [&](const char *what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[dkt tree] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
+    tprev = now;
+  };
   if (flags & DKT_ELEMS_ON_DEVICE) CK(cudaDeviceSynchronize());  // the points may still be in flight on a stream of the caller's
   TBuf<uint32_t> in;
   const uint32_t *src = pts;
@@ -373,6 +386,7 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
     if (rc) return rc;
   }
   in.release();
+  stage("point keys + sort");
   std::vector<uint64_t> qBegin(depth + 1, 0), qEnd(depth + 1, 0);  // Q_l = Qs[qBegin[l], qEnd[l])
   TBuf<uint64_t> Qs;
   uint64_t nQ = 0;
@@ -408,6 +422,7 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
     }
   }
   keys.release();
+  stage("split nodes Q");
 
   // ---- P: bottom-up over the levels ----------------------------------------------------------------------------------------
   const int nch = 1 << dim;
@@ -427,6 +442,7 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
     if (rc) return rc;
   }
   Qs.release();
+  stage("levels bottom-up (P)");
 
   // ---- leaves ----------------------------------------------------------------------------------------------------------------
   uint64_t nLeaves = 0;
@@ -461,6 +477,8 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
     }
   }
 
+  stage("leaves");
+
   // ---- tree order (SFC_Tree::locTreeSort, include/tsort.tcc:17-80) ----------------------------------------------------------
   SfcTables tab;
   make_sfc_tables(dim, tr.sfc_mode, tab);
@@ -486,6 +504,7 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
   TLAUNCH(k_gather_leaves, nLeaves, lxyz.p, llev.p, i1.p, nLeaves, dim, tr.d_xyz, tr.d_lev);
   CK(cudaStreamSynchronize(stream));
   CK(cudaGetLastError());
+  stage("tree order");
   tr.n = nLeaves;
   tr.finest_level = lmax;
   return DKT_OK;
