@@ -47,7 +47,19 @@ def run(name, xyz, lev, dim, order, md, steps=10, warm=3):
 
 
 def main():
-    which = sys.argv[1:] or ["c1", "c2a", "c2b", "c4", "cg"]
+    which = sys.argv[1:] or ["c1", "c2a", "c2b", "c3pts", "c4", "cg"]
+    if "c3pts" in which:
+        # SURVEY 8d C3 as the reference builds it: shell points + level-3 guard -> distTreeBalancing -> DA -> matvec, all on the GPU
+        pts = torch.from_numpy(dkt.trees.shell_points(4, 500000, 12, guard_level=3).astype(np.int64)).to(torch.int32).cuda()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        tr = dkt.Tree(pts, 4, 12, 1, balance=True)
+        torch.cuda.synchronize()
+        tt = time.time() - t0
+        x, l = tr.export_torch()
+        tr.close()
+        print(json.dumps({"config": "C3 tree pipeline", "n_points": int(pts.shape[0]), "leaves": int(l.numel()), "tree_build_s": round(tt, 4)}), flush=True)
+        run("C3 4-D p=1, shell points + guard through dkt_tree_from_points (distTreeBalancing)", x, l, 4, 1, 12)[0].close()
     if "c1" in which:
         x, l = dkt.trees.moving_ball_tree(2, 14, 16, use_torch=True)
         run("C1 2-D p=1 adaptive ball level 14", x, l, 2, 1, 16)[0].close()

@@ -11,5 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2> $O/ncu2.err
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mvf -s 6 -c 1 -f -o $O/prof_mvf \
   python bench.py --steps 3 --warmup 1 --no-cpu-baseline > $O/ncu_full.log 2>&1
-timeout 300 python tools/bench_configs.py > $O/configs.txt 2>&1; cat $O/configs.txt
+timeout 400 python tools/bench_configs.py > $O/configs.txt 2>&1; cat $O/configs.txt
+# one GPU at the per-GPU size of an 8x larger job (the N=8 bench tree on ONE device): 9.7e7 elements
+timeout 600 python bench.py --per-gpu-elems 9.6e7 --no-cpu-baseline > $O/bench_large.json 2> $O/bench_large.err; head -c 700 $O/bench_large.json; echo
 ls -la $O
