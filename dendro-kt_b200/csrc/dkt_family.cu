@@ -30,6 +30,15 @@ namespace dkt
 #ifndef DKT_FAM_EXP
 #define DKT_FAM_EXP 0      // timing experiments only (wrong results): 1 no node phase, 2 no hanging-node code, 4 no operator, 8 no gather, 16 no RED
 #endif
+#ifndef DKT_FAM_PF
+#define DKT_FAM_PF 600   // > 0: every CTA prefetches the tables of chunk c + DKT_FAM_PF into L2 (cp.async.bulk.prefetch.L2)
+#endif
+#ifndef DKT_FAM_NB
+#define DKT_FAM_NB 2     // nodes a thread of the node phase handles at a time
+#endif
+#ifndef DKT_FAM_TAU
+#define DKT_FAM_TAU 1    // 1: quirk-Q1 scalar as FMAs with bit-masked weights instead of predicated adds
+#endif
 #ifndef DKT_FAM_MINB
 #define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
@@ -64,6 +73,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
   const uint32_t a = smem_u32(bar);
@@ -84,6 +97,7 @@ inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
   memcpy(dst, src, bytes);
   *bar += (uint64_t)bytes << 32;
 }
+inline void bulk_prefetch_l2(const void *, uint32_t) {}
 inline void mbar_wait(uint64_t *bar, uint32_t)
 {
   while ((uint32_t)*bar == 0 || (*bar >> 32) + 1 < (uint32_t)*bar) emu::spin_yield();
@@ -173,6 +187,16 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     bulk_g2s(rec, p.rec + noff, recBytes, bar + 1);
     bulk_g2s(inv, p.inv16 + (uint64_t)c * (UPC * L), slotBytes, bar + 1);
     bulk_g2s(jd, p.jd + (uint64_t)c * (2 * p.jdStride), jdBytes, bar + 1);
+#if DKT_FAM_PF
+    const uint32_t cp = c + DKT_FAM_PF;
+    if (cp < p.nChunks)
+    {
+      bulk_prefetch_l2(p.slotw + (uint64_t)cp * (UPC * L), 2 * slotBytes);
+      bulk_prefetch_l2(p.frec + (uint64_t)cp * (UPC * 4), frecBytes);
+      bulk_prefetch_l2(p.inv16 + (uint64_t)cp * (UPC * L), slotBytes);
+      bulk_prefetch_l2(p.rec + p.node_off[cp], (uint32_t)((p.nloc[cp] + 3) & ~3u) * 4u);
+    }
+#endif
   }
   (void)un;
   mbar_wait(bar, 0);  // slot words and family records
@@ -211,7 +235,6 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     const int f = fw0 + (act ? fl : 0);
     const int c2 = j & 1, c3 = (j >> 1) & 1;
     double *Lf = Ls + f * S;
-    const uint16_t *rkf = rk + f * L;
     const uint32_t *fr = frec + f * 4;
     // the quad's lattice points: 9 (i0, i1) x (s2, s3); s_d = 0: the corner side p_d = 2 c_d, s_d = 1: the middle p_d = 1
     int boff[NS];        // shared-memory offset of the points with (s2, s3)
@@ -363,6 +386,20 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
       if (hangfam)
       {
         // quirk Q1 on a family (see k_family_check): tau = sum over the child's hanging ranks of 2^-|odd| eout, off its corner
+#if DKT_FAM_TAU
+        // the weight 2^-|odd| is a power of two: its bit pattern is all in the high word, which the hanging bit multiplies
+        double tau = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; r++)
+        {
+          const int i0 = c0 + (r & 1), i1 = c1 + ((r >> 1) & 1), sg = r >> 2;
+          const int nodd = (i0 == 1) + (i1 == 1) + (sg & 1) + (sg >> 1);
+          if (nodd == 0 || nodd == DIM) continue;  // the corner itself
+          const uint32_t hi = ((g[sg] >> (i0 + 3 * i1)) & 1u) * (uint32_t)(0x3FF00000u - ((uint32_t)nodd << 20));
+          tau = fma(__hiloint2double((int)hi, 0), e[r], tau);
+        }
+        e[c0 | (c1 << 1)] -= tau;
+#else
         double tk[DIM] = {};  // sums of the hanging ranks with 1, 2, .. odd coordinates (the centre, all odd, never hangs)
 #pragma unroll
         for (int r = 0; r < N; r++)
@@ -376,6 +413,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
 #pragma unroll
         for (int k = DIM - 2; k >= 0; k--) tau = fma(1.0 / (double)(2 << k), tk[k], tau);
         e[c0 | (c1 << 1)] -= tau;
+#endif
       }
 #pragma unroll
       for (int r = 0; r < N; r++)
@@ -466,21 +504,25 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     const int cn[4] = {cnt0, (int)cnt[1], (int)cnt[2], (int)cnt[3]};
     const int jo[4] = {0, (int)jd[1], (int)jd[2], (int)jd[3]};
     const char *Lb = (const char *)Ls;
-    for (int base = tid; base < cnt0; base += 2 * TPB)
+    constexpr int NB = DKT_FAM_NB;
+    for (int base = tid; base < cnt0; base += NB * TPB)
     {
-      uint32_t ix[2][4];
-      double v[2][4];
+      uint32_t ix[NB][4], rc[NB];
+      double v[NB][4];
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+      for (int h = 0; h < NB; h++)
+      {
+        const int n = base + h * TPB;
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
-          const int n = base + h * TPB;
           ix[h][k] = 0;
           if (n < cn[k]) ix[h][k] = inv[jo[k] + n];
         }
+        rc[h] = n < cnt0 ? rec[n] : 0u;
+      }
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+      for (int h = 0; h < NB; h++)
 #pragma unroll
         for (int k = 0; k < 4; k++)
         {
@@ -489,12 +531,12 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
           if (n < cn[k]) v[h][k] = *(const double *)(Lb + ix[h][k]);
         }
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+      for (int h = 0; h < NB; h++)
       {
         const int n = base + h * TPB;
         if (n >= cnt0) continue;
         const double a = (v[h][0] + v[h][1]) + (v[h][2] + v[h][3]);
-        const uint32_t r = rec[n];
+        const uint32_t r = rc[h];
         if (DIRI && (r & REC_BDY)) continue;
         double *dst = p.out + (r >> 2);
         if ((r & REC_SHARED) && !(DKT_FAM_EXP & 16)) atomicAdd(dst, a);

@@ -149,6 +149,7 @@ template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; retur
 template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+inline double __hiloint2double(int hi, int lo) { const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double r; memcpy(&r, &b, 8); return r; }
 // warp shuffle between the fibers of one warp: post, wait for the partner's post, read, wait until the partner has read
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o)
 {
