@@ -257,8 +257,7 @@ extern "C"
   int dkt_da_export_elements(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
-    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
-    const DA &d = da->d;
+    const DA &d = da->d;  // partitioned DA: the WHOLE tree in tree order (every rank holds it)
     CKA(cudaSetDevice(d.device));
     D2H(xyz, d.d_elem_xyz, d.nElem * d.dim * sizeof(uint32_t));
     D2H(lev, d.d_elem_lev, d.nElem);
@@ -267,8 +266,7 @@ extern "C"
   int dkt_da_export_nodes(const dkt_da *da, uint32_t *xyz, uint8_t *lev)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
-    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
-    const DA &d = da->d;
+    const DA &d = da->d;  // partitioned DA: the local vector [owned | ghosts], n_nodes + n_ghost_nodes entries
     CKA(cudaSetDevice(d.device));
     D2H(xyz, d.d_node_xyz, d.nNodes * d.dim * sizeof(uint32_t));
     D2H(lev, d.d_node_lev, d.nNodes);
@@ -277,8 +275,7 @@ extern "C"
   int dkt_da_export_boundary(const dkt_da *da, uint32_t *ids)
   {
     if (!da) { set_error("NULL da"); return DKT_ERR_INVALID; }
-    if (da->dist.active) { set_error("table exports are available on single-rank DAs only"); return DKT_ERR_UNSUPPORTED; }
-    const DA &d = da->d;
+    const DA &d = da->d;  // partitioned DA: the OWNED nodes on the domain boundary (local indices)
     CKA(cudaSetDevice(d.device));
     D2H(ids, d.d_bdy, d.nBdy * sizeof(uint32_t));
     return DKT_OK;
@@ -366,6 +363,32 @@ extern "C"
     return da->dist.active ? ghost_exchange_end(da->d, da->dist) : DKT_OK;
   }
   int dkt_ghost_write_end(dkt_da *da, double *vec) { return dkt_ghost_read_end(da, vec); }
+  // the same exchanges on a HOST vector [owned | ghosts] (what DA::readFromGhostBegin/End get from an application)
+  static int ghost_host(dkt_da *da, double *vec, int which)
+  {
+    if (!da || !vec) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    if (!da->dist.active || da->dist.nranks <= 1) return DKT_OK;
+    DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    const size_t nO = da->dist.nOwned, nG = da->dist.nGhost;
+    double *tmp = nullptr;
+    CKA(cudaMalloc((void **)&tmp, std::max<size_t>(nO + nG, 1) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(tmp, vec, (nO + nG) * sizeof(double), cudaMemcpyHostToDevice, d.stream);
+    int rc = e == cudaSuccess ? ghost_exchange_begin(d, da->dist, tmp, which) : DKT_ERR_CUDA;
+    if (rc == DKT_OK) rc = ghost_exchange_end(d, da->dist);
+    if (rc == DKT_OK)
+    {
+      // read: the ghost segment changed; write: the owned segment accumulated what came back
+      e = which == 0 ? cudaMemcpyAsync(vec + nO, tmp + nO, nG * sizeof(double), cudaMemcpyDeviceToHost, d.stream)
+                     : cudaMemcpyAsync(vec, tmp, nO * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+      if (e != cudaSuccess) { set_error(std::string("ghost exchange: ") + cudaGetErrorString(e)); rc = DKT_ERR_CUDA; }
+    }
+    cudaFree(tmp);
+    return rc;
+  }
+  int dkt_ghost_read_host(dkt_da *da, double *vec) { return ghost_host(da, vec, 0); }
+  int dkt_ghost_write_host(dkt_da *da, double *vec) { return ghost_host(da, vec, 1); }
 
   int dkt_cg_solve(dkt_da *da, const dkt_op *op, double *x, const double *b, int max_iter, double *tol, double scale,
                    unsigned flags, int *iters, int *status)

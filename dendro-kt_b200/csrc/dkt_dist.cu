@@ -176,6 +176,12 @@ __global__ void k_remap(const uint32_t *in, uint64_t n, const uint32_t *g2l, uin
   const uint32_t v = in[i];
   out[i] = v == INVALID ? INVALID : g2l[v];
 }
+__global__ void k_gather_rows32(const uint32_t *src, const uint32_t *idx, uint64_t n, int width, uint32_t *dst)
+{
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  dst[t] = src[(uint64_t)idx[t / width] * width + t % width];
+}
 __global__ void k_gather_u8(const uint8_t *in, const uint32_t *idx, uint64_t n, uint8_t *out)
 {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -561,8 +567,27 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   CK(cudaMemcpyAsync(srcL + nRegL, g.d_mv_src + nReg + h0, nHangL * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
   CK(cudaMemcpyAsync(childL, g.d_child + h0, nHangL, cudaMemcpyDeviceToDevice, g.stream));
   LAUNCHS(k_gather_u8, nLocal, g.stream, g.d_node_isbdy, l2g, nLocal, bdyL);
+  // node coordinates / levels of the local vector [owned | ghosts] (DA::getTNCoords of a rank, src/oda.cpp:131-140) and the owned
+  // nodes on the domain boundary (DA::getBoundaryNodeIndices): what dkt_da_export_nodes / _boundary return on a partitioned DA
+  uint32_t *nodeXyzL = nullptr, *bdyIdsL = nullptr;
+  uint8_t *nodeLevL = nullptr;
+  uint64_t nBdyOwned = 0;
+  CK(cudaMalloc((void **)&nodeXyzL, std::max<uint64_t>(nLocal, 1) * dim * sizeof(uint32_t)));
+  CK(cudaMalloc((void **)&nodeLevL, std::max<uint64_t>(nLocal, 1)));
+  LAUNCHS(k_gather_rows32, nLocal * dim, g.stream, g.d_node_xyz, l2g, nLocal, dim, nodeXyzL);
+  LAUNCHS(k_gather_u8, nLocal, g.stream, g.d_node_lev, l2g, nLocal, nodeLevL);
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaGetLastError());
+  {
+    std::vector<uint8_t> hb(nOwned);
+    if (nOwned) CK(cudaMemcpy(hb.data(), bdyL, nOwned, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> ids;
+    for (uint64_t i = 0; i < nOwned; i++)
+      if (hb[i]) ids.push_back((uint32_t)i);
+    nBdyOwned = ids.size();
+    CK(cudaMalloc((void **)&bdyIdsL, std::max<uint64_t>(nBdyOwned, 1) * sizeof(uint32_t)));
+    if (nBdyOwned) CK(cudaMemcpy(bdyIdsL, ids.data(), nBdyOwned * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
 
   // ---- [interior | boundary] order inside the regular and the hanging list, so that interior elements can
   //      run while the ghost exchanges are in flight --------------------------------------------------------------
@@ -630,6 +655,8 @@ int partition_da(DA &g, Dist &dist, int rank, int nranks, const void *nccl_id)
   // ---- swap the global tables for the local ones -------------------------------------------------------------------
   cudaFree(g.d_e2n); cudaFree(g.d_pnode); cudaFree(g.d_mv_xyz); cudaFree(g.d_mv_src); cudaFree(g.d_mv_lev); cudaFree(g.d_child);
   cudaFree(g.d_node_isbdy); cudaFree(g.d_ukey); cudaFree(g.d_unode);
+  cudaFree(g.d_node_xyz); cudaFree(g.d_node_lev); cudaFree(g.d_bdy);
+  g.d_node_xyz = nodeXyzL; g.d_node_lev = nodeLevL; g.d_bdy = bdyIdsL; g.nBdy = nBdyOwned;
   g.d_ukey = nullptr; g.d_unode = nullptr;
   g.d_e2n = e2nL; g.d_pnode = pnodeL; g.d_mv_xyz = xyzL; g.d_mv_src = srcL; g.d_mv_lev = levL; g.d_child = childL;
   g.d_node_isbdy = bdyL;

@@ -27,7 +27,7 @@ DECLARED_SYMBOLS = [
     "dkt_nccl_unique_id", "dkt_da_create_dist", "dkt_p2p_attach_local", "dkt_da_export_owned_ids", "dkt_da_export_exchange",
     "dkt_da_export_elements", "dkt_da_export_nodes", "dkt_da_export_boundary", "dkt_da_export_tables", "dkt_matvec",
     "dkt_cg_solve", "dkt_ghost_read_begin", "dkt_ghost_read_end", "dkt_ghost_write_begin", "dkt_ghost_write_end", "dkt_last_kernel_ms", "dkt_da_chunk_info", "dkt_da_stream", "dkt_da_set_stream", "dkt_kernel_launch_count",
-    "dkt_tree_from_points", "dkt_tree_size", "dkt_tree_export", "dkt_tree_device_ptrs", "dkt_tree_destroy",
+    "dkt_ghost_read_host", "dkt_ghost_write_host", "dkt_tree_from_points", "dkt_tree_size", "dkt_tree_export", "dkt_tree_device_ptrs", "dkt_tree_destroy",
 ]
 
 

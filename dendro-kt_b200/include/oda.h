@@ -26,6 +26,7 @@ class DA
   unsigned int m_uiElementOrder = 1, m_uiNpE = 0;
   unsigned int m_uiTotalNodalSz = 0, m_uiLocalNodalSz = 0, m_uiLocalNodeBegin = 0, m_uiGlobalNodeSz = 0;
   unsigned int m_uiLocalElementSz = 0;
+  int m_rank = 0, m_nranks = 1;
   MPI_Comm m_uiGlobalComm = MPI_COMM_WORLD;
   std::vector<TreeNode<C, dim>> m_tnCoords;
   TreeNode<C, dim> m_treePartFront, m_treePartBack;
@@ -101,24 +102,57 @@ public:
       for (unsigned d = 0; d < dim; d++) xyz[(size_t)i * dim + d] = inTree[i].getX(d);
       lev[i] = (uint8_t)inTree[i].getLevel();
     }
-    dkt_host::check(dkt_da_create(dim, order, m_uiMaxDepth, sfcMode, xyz.data(), lev.data(), nEle, ip0, ip1, 0u, &m_handle), "DA::construct");
+    // Several ranks (one process per GPU): the DA is partitioned - SFC-contiguous element ranges, owned + ghost nodes, exchanges
+    // over NCCL (dkt_da_create_dist).  The library partitions a tree that every rank holds in full: with MPI the ranks' pieces
+    // (the reference's distributed tree) are gathered first; without MPI every rank must pass the whole tree.
+    dkt_host::comm_rank_size(comm, m_rank, m_nranks);
+    if (m_nranks > 1)
+    {
+#if defined(MPI_VERSION) || defined(DKT_HAVE_MPI)
+      {
+        int cnt = (int)nEle;
+        std::vector<int> cnts(m_nranks), dx(m_nranks), dl(m_nranks), cx(m_nranks);
+        MPI_Allgather(&cnt, 1, MPI_INT, cnts.data(), 1, MPI_INT, comm);
+        size_t tot = 0;
+        for (int r = 0; r < m_nranks; r++) { dl[r] = (int)tot; dx[r] = (int)(tot * dim); cx[r] = cnts[r] * (int)dim; tot += cnts[r]; }
+        std::vector<uint32_t> ax(tot * dim);
+        std::vector<uint8_t> al(tot);
+        MPI_Allgatherv(xyz.data(), cnt * (int)dim, MPI_UNSIGNED, ax.data(), cx.data(), dx.data(), MPI_UNSIGNED, comm);
+        MPI_Allgatherv(lev.data(), cnt, MPI_UNSIGNED_CHAR, al.data(), cnts.data(), dl.data(), MPI_UNSIGNED_CHAR, comm);
+        xyz.swap(ax);
+        lev.swap(al);
+        nEle = (unsigned)tot;
+      }
+#endif
+      char id[128];
+      dkt_host::share_nccl_id(comm, m_rank, id);
+      dkt_host::check(dkt_da_create_dist(dim, order, m_uiMaxDepth, sfcMode, xyz.data(), lev.data(), nEle, ip0, ip1, 0u, m_rank, m_nranks, id,
+                                         &m_handle),
+                      "DA::construct");
+    }
+    else
+      dkt_host::check(dkt_da_create(dim, order, m_uiMaxDepth, sfcMode, xyz.data(), lev.data(), nEle, ip0, ip1, 0u, &m_handle), "DA::construct");
     dkt_host::check(dkt_da_sizes(m_handle, &m_sizes), "dkt_da_sizes");
     m_uiNpE = m_sizes.nodes_per_elem;
-    m_uiTotalNodalSz = m_uiLocalNodalSz = m_uiGlobalNodeSz = (unsigned)m_sizes.n_nodes;
+    // local vector layout [owned | ghosts]: getLocalNodeBegin() == 0, getPostNodalSz() == ghosts (the reference puts the ghosts owned by
+    // lower ranks in front, include/oda.h:180-200; applications address the layout through these getters)
+    m_uiLocalNodalSz = (unsigned)m_sizes.n_nodes;
+    m_uiTotalNodalSz = (unsigned)(m_sizes.n_nodes + m_sizes.n_ghost_nodes);
+    m_uiGlobalNodeSz = (unsigned)m_sizes.n_global_nodes;
     m_uiLocalNodeBegin = 0;
     m_uiLocalElementSz = nEle;
     // node coordinates in DA order (src/oda.cpp:131-140)
-    std::vector<uint32_t> nx((size_t)m_sizes.n_nodes * dim);
-    std::vector<uint8_t> nl(m_sizes.n_nodes);
+    std::vector<uint32_t> nx((size_t)m_uiTotalNodalSz * dim);
+    std::vector<uint8_t> nl(m_uiTotalNodalSz);
     dkt_host::check(dkt_da_export_nodes(m_handle, nx.data(), nl.data()), "dkt_da_export_nodes");
-    m_tnCoords.resize(m_sizes.n_nodes);
+    m_tnCoords.resize(m_uiTotalNodalSz);
     for (size_t i = 0; i < m_tnCoords.size(); i++)
     {
       std::array<C, dim> c;
       for (unsigned d = 0; d < dim; d++) c[d] = nx[i * dim + d];
       m_tnCoords[i] = TreeNode<C, dim>(1, c, nl[i]);
     }
-    // splitters (src/oda.cpp:85-86): first and last element of the sorted tree
+    // splitters (src/oda.cpp:85-86): first and last element of the sorted tree (of the whole tree, also on a partitioned DA)
     dkt_host::check(dkt_da_export_elements(m_handle, xyz.data(), lev.data()), "dkt_da_export_elements");
     auto elem = [&](size_t i) {
       std::array<C, dim> c;
@@ -135,7 +169,7 @@ public:
   unsigned int getLocalNodalSz() const { return m_uiLocalNodalSz; }
   unsigned int getLocalNodeBegin() const { return m_uiLocalNodeBegin; }
   unsigned int getPreNodalSz() const { return 0; }
-  unsigned int getPostNodalSz() const { return 0; }
+  unsigned int getPostNodalSz() const { return m_uiTotalNodalSz - m_uiLocalNodalSz; }
   unsigned int getTotalNodalSz() const { return m_uiTotalNodalSz; }
   unsigned int getGlobalNodeSz() const { return m_uiGlobalNodeSz; }
   unsigned int getGlobalRankBegin() const { return 0; }
@@ -145,10 +179,19 @@ public:
   unsigned int getElementOrder() const { return m_uiElementOrder; }
   MPI_Comm getGlobalComm() const { return m_uiGlobalComm; }
   MPI_Comm getCommActive() const { return m_uiGlobalComm; }
-  unsigned int getNpesAll() const { return 1; }
-  unsigned int getNpesActive() const { return 1; }
-  unsigned int getRankAll() const { return 0; }
-  unsigned int getRankActive() const { return 0; }
+  unsigned int getNpesAll() const { return (unsigned)m_nranks; }
+  unsigned int getNpesActive() const { return (unsigned)m_nranks; }
+  unsigned int getRankAll() const { return (unsigned)m_rank; }
+  unsigned int getRankActive() const { return (unsigned)m_rank; }
+  /** partitioned DA: position of every owned node in the single-rank DA order (the order the oracle and the fixtures use) */
+  std::vector<unsigned int> getOwnedGlobalIds() const
+  {
+    std::vector<unsigned int> ids(m_uiLocalNodalSz);
+    if (m_nranks > 1) dkt_host::check(dkt_da_export_owned_ids(m_handle, ids.data()), "dkt_da_export_owned_ids");
+    else
+      for (unsigned i = 0; i < m_uiLocalNodalSz; i++) ids[i] = i;
+    return ids;
+  }
   unsigned int getMaxDepth() const { return m_uiMaxDepth; }
   unsigned int getDimension() const { return dim; }
   const TreeNode<C, dim> *getTNCoords() const { return m_tnCoords.data(); }
@@ -193,9 +236,10 @@ public:
     if (!isAllocated) createVector(local, false, false, dof);
     std::memcpy(local, gVec + (size_t)dof * m_uiLocalNodeBegin, sizeof(T) * dof * m_uiLocalNodalSz);
   }
-  // Ghost exchanges (include/oda.h:300-322).  One process drives one GPU: a DA made by these constructors is a single-rank DA and
-  // the exchanges are no-ops exactly as in the reference at one rank (include/oda.tcc:216,283,324,387).  For a partitioned DA
-  // (dkt_da_create_dist) the C ABI carries them: dkt_ghost_read_begin/end, dkt_ghost_write_begin/end on device vectors.
+  // Ghost exchanges on HOST vectors of getTotalNodalSz() entries (include/oda.h:300-322).  One rank: no-ops exactly as in the
+  // reference (include/oda.tcc:216,283,324,387).  Several ranks: Begin performs the exchange over NCCL (dkt_ghost_read_host /
+  // dkt_ghost_write_host: upload, exchange, download of the changed segment), End has nothing left to wait for.  Resident device
+  // vectors use dkt_ghost_read_begin/end, dkt_ghost_write_begin/end of the C ABI instead.
   template <typename T> void readFromGhostBegin(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 0, true); }
   template <typename T> void readFromGhostEnd(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 0, false); }
   template <typename T> void writeToGhostsBegin(T *vec, unsigned int dof = 1) { ghostOp(vec, dof, 1, true); }
@@ -207,10 +251,9 @@ private:
   {
     if (m_sizes.n_ranks <= 1) return;
     if (dof != 1 || !std::is_same<T, double>::value) throw std::runtime_error("ghost exchange: dof == 1, double vectors");
+    if (!begin) return;
     double *v = reinterpret_cast<double *>(vec);
-    const int rc = which == 0 ? (begin ? dkt_ghost_read_begin(m_handle, v) : dkt_ghost_read_end(m_handle, v))
-                              : (begin ? dkt_ghost_write_begin(m_handle, v) : dkt_ghost_write_end(m_handle, v));
-    dkt_host::check(rc, "ghost exchange");
+    dkt_host::check(which == 0 ? dkt_ghost_read_host(m_handle, v) : dkt_ghost_write_host(m_handle, v), "ghost exchange");
   }
 };
 } // namespace ot

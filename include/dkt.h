@@ -159,9 +159,11 @@ int dkt_da_export_exchange(const dkt_da *da, uint64_t *send_counts, uint64_t *re
 int dkt_da_sizes(const dkt_da *da, dkt_sizes *out);
 /* tree in DA order: what DA::getTreePartFront()/Back() bracket (include/oda.h:255-258) */
 int dkt_da_export_elements(const dkt_da *da, uint32_t *xyz, uint8_t *lev);
-/* DA::getTNCoords() (include/oda.h:252): node coordinates and levels in DA order */
+/* DA::getTNCoords() (include/oda.h:252): node coordinates and levels in DA order; partitioned DA: of the local vector
+ * [owned | ghosts], n_nodes + n_ghost_nodes entries */
 int dkt_da_export_nodes(const dkt_da *da, uint32_t *xyz, uint8_t *lev);
-/* DA::getBoundaryNodeIndices() (include/oda.h:264) */
+/* DA::getBoundaryNodeIndices() (include/oda.h:264); partitioned DA: the owned boundary nodes, local indices
+ * (dkt_sizes.n_boundary of them) */
 int dkt_da_export_boundary(const dkt_da *da, uint32_t *ids);
 /* flat tables (no reference counterpart - the reference re-discovers them every matvec,
  * FEM/include/matvec.h:244-548).  Visited elements are stored regular-first: entries
@@ -206,6 +208,11 @@ int dkt_ghost_read_begin(dkt_da *da, double *vec);
 int dkt_ghost_read_end(dkt_da *da, double *vec);
 int dkt_ghost_write_begin(dkt_da *da, double *vec);
 int dkt_ghost_write_end(dkt_da *da, double *vec);
+/* The same on HOST vectors of n_nodes + n_ghost_nodes doubles (blocking): what an application hands to
+ * DA::readFromGhostBegin/End and writeToGhostsBegin/End.  read: fills the ghost segment; write: adds the ghost segment's
+ * values to their owners' entries in the owned segment. */
+int dkt_ghost_read_host(dkt_da *da, double *vec);
+int dkt_ghost_write_host(dkt_da *da, double *vec);
 /* Diagnostics of the chunked tables: out[0..4] = regular per-element sets {chunks, units per chunk, max nodes per
  * chunk, max run length, total chunk nodes}, out[5..9] = the same for the hanging per-element sets, out[10..14] for
  * the sibling-family sets (unit = family), out[15] = elements inside sibling families. */

@@ -34,6 +34,14 @@ def test_tsort_header_compiles(dkt, tmp_path):
     assert rc.returncode == 0 or "no CUDA device" in rc.stderr  # no CPU path: on a box without a GPU the library refuses loudly
 
 
+def test_dist_api_program_compiles(dkt, tmp_path):
+    """CPU: the multi-rank test program (ot::DA partitioned over ranks, ghost exchanges) compiles warning-free; it runs in
+    tests/test_gpu_dist.py on a box with at least two GPUs."""
+    out = str(tmp_path / "test_dist_api")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-I", INC, os.path.join(ROOT, "tests", "cpp", "test_dist_api.cpp"), "-o", out,
+                           "-L", LIBDIR, "-ldkt", "-Wl,-rpath," + LIBDIR])
+
+
 def test_host_api_compiles(host_api_binary):
     """CPU: the header-only host layer compiles warning-free against the C ABI and links to libdkt.so."""
     assert os.path.exists(host_api_binary)
