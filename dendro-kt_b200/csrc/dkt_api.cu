@@ -58,6 +58,20 @@ struct dkt_tree
     }                                                                                             \
   } while (0)
 
+// interleaved [node][component] <-> component-major [component][node]
+__global__ void k_dof_split(const double *in, size_t n, int dof, double *out)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n * dof) return;
+  out[(i % dof) * n + i / dof] = in[i];
+}
+__global__ void k_dof_merge(const double *in, size_t n, int dof, double *out)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n * dof) return;
+  out[i] = in[(i % dof) * n + i / dof];
+}
+
 extern "C"
 {
   const char *dkt_last_error(void) { return g_err.c_str(); }
@@ -342,6 +356,60 @@ extern "C"
     if (!(flags & DKT_VEC_DEVICE))
     {
       CKA(cudaMemcpyAsync(out, d.d_out, bytes, cudaMemcpyDeviceToHost, d.stream));
+      CKA(cudaStreamSynchronize(d.stream));
+    }
+    return DKT_OK;
+  }
+
+  // dof > 1: vectors interleaved per node, [abc][abc].. (include/oda.h:296-322), the elemental operator applied to
+  // every component.  The components are split into contiguous vectors, each takes the scalar path, and the results are merged:
+  // the cost per DOF is the scalar one plus two streaming passes.
+  int dkt_matvec_dof(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags, int dof)
+  {
+    if (dof == 1) return dkt_matvec(da, op, in, out, scale, flags);
+    if (!da || !op || !in || !out) { set_error("NULL argument"); return DKT_ERR_INVALID; }
+    if (dof < 1 || dof > 64) { set_error("dof must be in 1..64"); return DKT_ERR_INVALID; }
+    if (flags & DKT_VEC_GHOSTED) { set_error("dkt_matvec_dof takes owned-length vectors"); return DKT_ERR_INVALID; }
+    DA &d = da->d;
+    CKA(cudaSetDevice(d.device));
+    const size_t n = da->dist.active ? da->dist.nOwned : d.nNodes, tot = n * (size_t)dof;
+    const bool host = !(flags & DKT_VEC_DEVICE);
+    const size_t need = (host ? 3 : 2) * tot;
+    if (d.dof_cap < need)
+    {
+      cudaFree(d.d_dof);
+      d.d_dof = nullptr;
+      d.dof_cap = 0;
+      CKA(cudaMalloc((void **)&d.d_dof, std::max<size_t>(need, 1) * sizeof(double)));
+      d.dof_cap = need;
+    }
+    double *cin = d.d_dof, *cout = d.d_dof + tot, *stage = d.d_dof + 2 * tot;
+    const double *src = in;
+    if (host)
+    {
+      CKA(cudaMemcpyAsync(stage, in, tot * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+      src = stage;
+    }
+    if (tot)
+    {
+      k_dof_split<<<(unsigned)((tot + 255) / 256), 256, 0, d.stream>>>(src, n, dof, cin);
+      g_launches++;
+    }
+    for (int k = 0; k < dof; k++)
+    {
+      const int rc = dkt_matvec(da, op, cin + (size_t)k * n, cout + (size_t)k * n, scale, flags | DKT_VEC_DEVICE);
+      if (rc != DKT_OK) return rc;
+    }
+    double *dst = host ? stage : out;
+    if (tot)
+    {
+      k_dof_merge<<<(unsigned)((tot + 255) / 256), 256, 0, d.stream>>>(cout, n, dof, dst);
+      g_launches++;
+    }
+    CKA(cudaGetLastError());
+    if (host)
+    {
+      CKA(cudaMemcpyAsync(out, stage, tot * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
       CKA(cudaStreamSynchronize(d.stream));
     }
     return DKT_OK;

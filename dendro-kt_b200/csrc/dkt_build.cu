@@ -597,7 +597,7 @@ void free_da(DA &da)
   cudaFree(da.d_elem_xyz); cudaFree(da.d_elem_lev); cudaFree(da.d_node_xyz); cudaFree(da.d_node_lev);
   cudaFree(da.d_bdy); cudaFree(da.d_node_isbdy); cudaFree(da.d_node_sent); cudaFree(da.d_e2n); cudaFree(da.d_mv_lev); cudaFree(da.d_mv_src);
   cudaFree(da.d_mv_xyz); cudaFree(da.d_pnode); cudaFree(da.d_child); cudaFree(da.d_ukey); cudaFree(da.d_unode);
-  cudaFree(da.d_in); cudaFree(da.d_out); cudaFree(da.d_kbuf);
+  cudaFree(da.d_in); cudaFree(da.d_out); cudaFree(da.d_kbuf); cudaFree(da.d_dof);
   if (da.ev0) cudaEventDestroy(da.ev0);
   if (da.ev1) cudaEventDestroy(da.ev1);
   if (da.own_stream) cudaStreamDestroy(da.own_stream);

@@ -121,6 +121,8 @@ struct DA
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_AUX] = {nullptr, nullptr, nullptr};
 
   double *d_in = nullptr, *d_out = nullptr;  // staging for host-pointer matvecs
+  double *d_dof = nullptr;         // dkt_matvec_dof: component-major copies [in: dof x n | out: dof x n | host staging: n x dof]
+  size_t dof_cap = 0;              // doubles allocated in d_dof
   double *d_kbuf = nullptr;        // operator matrix of the 81-node (4-D order 2) flat kernels
   cudaStream_t stream = nullptr;      // stream in use (own_stream or the caller's)
   cudaStream_t own_stream = nullptr;

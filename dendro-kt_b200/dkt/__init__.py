@@ -27,7 +27,7 @@ DECLARED_SYMBOLS = [
     "dkt_nccl_unique_id", "dkt_da_create_dist", "dkt_p2p_attach_local", "dkt_da_export_owned_ids", "dkt_da_export_exchange",
     "dkt_da_export_elements", "dkt_da_export_nodes", "dkt_da_export_boundary", "dkt_da_export_tables", "dkt_matvec",
     "dkt_cg_solve", "dkt_ghost_read_begin", "dkt_ghost_read_end", "dkt_ghost_write_begin", "dkt_ghost_write_end", "dkt_last_kernel_ms", "dkt_da_chunk_info", "dkt_da_stream", "dkt_da_set_stream", "dkt_kernel_launch_count",
-    "dkt_ghost_read_host", "dkt_ghost_write_host", "dkt_tree_from_points", "dkt_tree_size", "dkt_tree_export", "dkt_tree_device_ptrs", "dkt_tree_destroy",
+    "dkt_ghost_read_host", "dkt_ghost_write_host", "dkt_matvec_dof", "dkt_tree_from_points", "dkt_tree_size", "dkt_tree_export", "dkt_tree_device_ptrs", "dkt_tree_destroy",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.dkt_da_export_boundary.argtypes = [vp, vp]
     L.dkt_da_export_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.dkt_matvec.argtypes = [vp, C.POINTER(_Op), vp, vp, f64, u32]
+    L.dkt_matvec_dof.argtypes = [vp, C.POINTER(_Op), vp, vp, f64, u32, i32]
     L.dkt_cg_solve.argtypes = [vp, C.POINTER(_Op), vp, vp, i32, C.POINTER(f64), f64, u32, C.POINTER(i32), C.POINTER(i32)]
     L.dkt_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.dkt_da_stream.restype = vp
@@ -310,9 +311,10 @@ class DA:
         return out
 
     # --- the hot path -----------------------------------------------------------------------------
-    def matvec(self, op, u, out=None, scale=1.0, q1_mask=True, flat=False, fastpath=True, ghosted=False):
+    def matvec(self, op, u, out=None, scale=1.0, q1_mask=True, flat=False, fastpath=True, ghosted=False, dof=1):
         """feMatrix::matVec(in, out, scale).  numpy arrays (host path: H2D + kernels + D2H inside the
-        call) or CUDA torch tensors (device path: kernels only, asynchronous on self.stream)."""
+        call) or CUDA torch tensors (device path: kernels only, asynchronous on self.stream).
+        dof > 1: u holds dof values per node, interleaved ([abc][abc]..), the operator acts on every component."""
         flags = (0 if q1_mask else NO_Q1_MASK) | (MV_FLAT if flat else 0) | (0 if fastpath else MV_NO_FASTPATH)
         if _is_cuda(u):
             import torch
@@ -321,16 +323,19 @@ class DA:
             if not getattr(self, "_user_stream", False):
                 # the DA launches on its own stream: order it after the work that produced `u`
                 torch.cuda.current_stream().synchronize()
-            want = self.n_nodes + (self.n_ghost_nodes if ghosted else 0)
+            want = (self.n_nodes + (self.n_ghost_nodes if ghosted else 0)) * dof
             assert u.dtype == torch.float64 and u.is_contiguous() and out.is_contiguous() and u.numel() == want == out.numel()
             flags |= VEC_DEVICE | (VEC_GHOSTED if ghosted else 0)
         else:
             u = np.ascontiguousarray(u, dtype=np.float64)
-            assert u.size == self.n_nodes
+            assert u.size == self.n_nodes * dof
             if out is None:
                 out = np.empty_like(u)
         c = op._c()
-        _check(lib().dkt_matvec(self._h, C.byref(c), _ptr(u), _ptr(out), float(scale), flags))
+        if dof != 1:
+            _check(lib().dkt_matvec_dof(self._h, C.byref(c), _ptr(u), _ptr(out), float(scale), flags, int(dof)))
+        else:
+            _check(lib().dkt_matvec(self._h, C.byref(c), _ptr(u), _ptr(out), float(scale), flags))
         return out
 
     def ghost_read(self, vec):

@@ -180,6 +180,10 @@ int dkt_da_export_tables(const dkt_da *da, uint32_t *mv_xyz, uint8_t *mv_lev, ui
  * stream (dkt_da_stream / dkt_da_set_stream) and the call returns without waiting; the caller orders that
  * stream after the producer of `in` and before the consumer of `out`. */
 int dkt_matvec(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags);
+/* dof > 1 (include/oda.h:296-322: vectors interleaved per node, [abc][abc]..; FEM/include/feMatrix.h m_uiDof): in/out hold
+ * dof * n_nodes doubles, the elemental operator acts on every component.  The reference's own traversal stops at dof == 1
+ * ("matvec only supports dof==1 right now", FEM/include/matvec.h:27), so this is checked against dof scalar matvecs. */
+int dkt_matvec_dof(dkt_da *da, const dkt_op *op, const double *in, double *out, double scale, unsigned flags, int dof);
 
 /* Conjugate gradients with every vector resident in HBM: the solver of the reference's example
  * operator, HeatMat::cgSolve(x, b, max_iter, tol) (FEM/examples/src/heatMat.cpp:165-325) - same

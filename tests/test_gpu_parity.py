@@ -318,3 +318,33 @@ def test_class_u_tree_is_refused(dkt):
 def test_smoke_case(dkt):
     import smoke_case
     smoke_case.run(dkt)
+
+
+@pytest.mark.parametrize("name", ["ball-d4-p1-morton-5", "gauss-d3-p1-hilbert", "ball-d3-p2-morton-5"])
+def test_interleaved_dof_vectors(dkt, name):
+    """dof > 1 (include/oda.h:296-322 layout [abc][abc]..): every component gets the scalar operator.  The reference's traversal is
+    dof == 1 only (FEM/include/matvec.h:27), so each component is compared with the reference's scalar vector."""
+    import torch
+    case = load_case(name)
+    g = case["golden"]
+    da = dkt.DA(case["xyz"], case["lev"], case["dim"], case["order"], case["max_depth"], sfc=_sfc(dkt, case), ip0=g["ip0"], ip1=g["ip1"])
+    n = da.n_nodes
+    K = cases.dense_operator(case["dim"], case["order"])
+    u = cases.input_vector(n)
+    dof = 3
+    U = np.stack([u, -2.0 * u, u[::-1]], axis=1)  # (n, dof), C order = interleaved
+    op = dkt.Operator.dense(K, float(g["alpha"]))
+    want0 = g["v_dense"]
+    want2 = da.matvec(op, np.ascontiguousarray(u[::-1]), scale=float(g["scale"]))
+    for dev in (False, True):
+        if dev:
+            V = da.matvec(op, torch.from_numpy(U).cuda().reshape(-1), scale=float(g["scale"]), dof=dof)
+            torch.cuda.synchronize()
+            V = V.cpu().numpy().reshape(n, dof)
+        else:
+            V = da.matvec(op, U.reshape(-1), scale=float(g["scale"]), dof=dof).reshape(n, dof)
+        s = np.abs(want0).max()
+        assert np.abs(V[:, 0] - want0).max() <= TOL * s
+        assert np.abs(V[:, 1] + 2.0 * want0).max() <= 2 * TOL * s
+        assert np.abs(V[:, 2] - want2).max() <= TOL * np.abs(want2).max()
+    da.close()
