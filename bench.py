@@ -100,33 +100,64 @@ def golden_parity(dkt, rank, world, dist, bcast_id):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region: NVML polled every millisecond (nvidia_ml_py), `nvidia-smi` every
+    0.1 s where NVML is not importable.  mark() brackets the timed region; the summary uses the samples inside it (all samples
+    if the region was shorter than one polling interval)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.marks = index, [], False, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def _nvml_row(self):
+        n = self.nvml
+        sm = int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        bits = [0x8, 0x40, 0x20, 0x4]  # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap (nvml.h)
+        return [str(sm), str(self.max_sm)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
+            t = time.perf_counter()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append((t, self._nvml_row()))
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append((t, [c.strip() for c in out.split(",")]))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.001 if self.nvml is not None else 0.1)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        rows = [r for _, r in self.rows]
+        inside = [r for t, r in self.rows if len(self.marks) >= 2 and self.marks[0] <= t <= self.marks[-1]]
+        use = inside if inside else rows
+        sm = sorted(int(r[0]) for r in use if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        reasons = sorted({n for r in use if len(r) >= 6 for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": len(inside), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_run(steps, warmup, level=5):
@@ -325,11 +356,15 @@ def run_gpu(args):
     launches0 = dkt.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.mark()
     ev[0].record(stream)
     for i in range(args.steps):
         da.matvec(op, u, v, ghosted=ghosted)
         ev[i + 1].record(stream)
     barrier()
+    sampler.mark()
+    sampler.stop_flag = True  # the end-to-end loop below is host-synchronous: no polling thread beside it
+    sampler.join(timeout=2)
     launches = dkt.kernel_launch_count() - launches0
     my_ms = ev[0].elapsed_time(ev[-1]) / args.steps
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
@@ -358,8 +393,6 @@ def run_gpu(args):
         da.matvec(op, un, vn)  # synchronous: returns after the D2H copy has landed
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     check = float(np.abs(vn - v[:n].cpu().numpy()).max() / max(np.abs(vn).max(), 1e-300))
 
     peaks, peak_kind = measured_peaks()
