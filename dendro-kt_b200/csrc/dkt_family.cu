@@ -39,6 +39,9 @@ namespace dkt
 #ifndef DKT_FAM_TAU
 #define DKT_FAM_TAU 1    // 1: quirk-Q1 scalar as FMAs with bit-masked weights instead of predicated adds
 #endif
+#ifndef DKT_FAM_GU
+#define DKT_FAM_GU 2     // families whose slot words a lane loads before it issues their gathers
+#endif
 #ifndef DKT_FAM_MINB
 #define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
@@ -275,6 +278,33 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
 #else
         const uint16_t *rkw = rk + fw0 * L;
 #endif
+#if DKT_FAM_DIRECT == 1 && DKT_FAM_GU > 1
+        // DKT_FAM_GU families at a time: their slot words are loaded together, then the copies go out (the loads of one
+        // family would otherwise wait for each other's shared-memory latency)
+        if (fsub < FPI)
+          for (int fl2 = fsub; fl2 < nfw; fl2 += FPI * DKT_FAM_GU)
+          {
+            uint32_t w[DKT_FAM_GU][KT];
+#pragma unroll
+            for (int u = 0; u < DKT_FAM_GU; u++)
+#pragma unroll
+              for (int t = 0; t < KT; t++)
+              {
+                const int k = k0 + 32 * t, f2 = fl2 + u * FPI;
+                w[u][t] = (k < L && f2 < nfw) ? sww[f2 * L + k] : SLOTW_ABSENT;
+              }
+#pragma unroll
+            for (int u = 0; u < DKT_FAM_GU; u++)
+#pragma unroll
+              for (int t = 0; t < KT; t++)
+                if (!(w[u][t] & SLOTW_ABSENT))
+                {
+                  double *dst = Ls + (fw0 + fl2 + u * FPI) * S + la[t];
+                  if ((DIRI && (w[u][t] & SLOTW_BDY)) || (DKT_FAM_EXP & 8)) *dst = 0.0;
+                  else cp_async8(dst, p.in + (w[u][t] >> 2));
+                }
+          }
+#else
         if (fsub < FPI)
           for (int fl2 = fsub; fl2 < nfw; fl2 += FPI)
           {
@@ -296,6 +326,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
 #endif
             }
           }
+#endif
 #if DKT_FAM_DIRECT
         cp_async_commit();
         cp_async_wait_all();
