@@ -42,6 +42,9 @@ namespace dkt
 #ifndef DKT_FAM_GU
 #define DKT_FAM_GU 2     // families whose slot words a lane loads before it issues their gathers
 #endif
+#ifndef DKT_FAM_TP
+#define DKT_FAM_TP 1     // 1: transposed hanging-node passes as FMAs with bit-masked weights
+#endif
 #ifndef DKT_FAM_MINB
 #define DKT_FAM_MINB 4   // resident CTAs per SM the family kernel is compiled for (128 registers: 64 bytes of spills in 4-D)
 #endif
@@ -469,6 +472,40 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
     if (hangfam)
     {
       // transposed interpolation of the hanging points towards the corners, one dimension at a time
+#if DKT_FAM_TP
+      // weight 0.5 or 0 as a bit-masked high word: one FMA per target instead of an add and two selects (every lattice value
+      // of a hanging family is finite, so 0 * value is 0; 0.5 * value is exact, so the rounding is that of the add)
+#define DKT_HALF_IF(bit) __hiloint2double((int)((bit) * 0x3FE00000u), 0)
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i1 = 0; i1 < 3; i1++)
+        {
+          const double w = DKT_HALF_IF((g[sg] >> (1 + 3 * i1)) & 1u), m = acc[1 + 3 * i1 + 9 * sg];
+          acc[0 + 3 * i1 + 9 * sg] = fma(m, w, acc[0 + 3 * i1 + 9 * sg]);
+          acc[2 + 3 * i1 + 9 * sg] = fma(m, w, acc[2 + 3 * i1 + 9 * sg]);
+        }
+#pragma unroll
+      for (int sg = 0; sg < NS; sg++)
+#pragma unroll
+        for (int i0 = 0; i0 < 3; i0++)
+        {
+          const double w = DKT_HALF_IF((g[sg] >> (i0 + 3)) & 1u), m = acc[i0 + 3 + 9 * sg];
+          acc[i0 + 9 * sg] = fma(m, w, acc[i0 + 9 * sg]);
+          acc[i0 + 6 + 9 * sg] = fma(m, w, acc[i0 + 6 + 9 * sg]);
+        }
+#pragma unroll
+      for (int d = 0; d < NL; d++)
+#pragma unroll
+        for (int sg = 0; sg < NS; sg++)
+        {
+          if (!((sg >> d) & 1)) continue;
+#pragma unroll
+          for (int i = 0; i < 9; i++)
+            acc[i + 9 * (sg ^ (1 << d))] = fma(acc[i + 9 * sg], DKT_HALF_IF((g[sg] >> i) & 1u), acc[i + 9 * (sg ^ (1 << d))]);
+        }
+#undef DKT_HALF_IF
+#else
 #pragma unroll
       for (int sg = 0; sg < NS; sg++)
 #pragma unroll
@@ -498,6 +535,7 @@ __global__ void __launch_bounds__(Fam<DIM>::TPB, DKT_FAM_MINB) k_mvf(const __gri
 #pragma unroll
           for (int i = 0; i < 9; i++) fma_if(acc[i + 9 * (sg ^ (1 << d))], acc[i + 9 * sg], 0.5, (g[sg] >> i) & 1u);
         }
+#endif
     }
     __syncwarp();  // every lane of the warp has read its lattice points
     if (act)
