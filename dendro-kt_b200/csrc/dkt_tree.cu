@@ -145,10 +145,28 @@ __global__ void k_split_depth(const uint64_t *keys, uint64_t n, uint64_t m, int 
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int L = 0;
-  if (n > m)
+  if (n > m && m <= 32)
   {
+    // windows of m + 1 consecutive keys that contain i: the common prefix of a window's ends is shared by all of it
     const uint64_t j0 = i >= m ? i - m : 0, j1 = (i + m < n) ? i : n - 1 - m;
     for (uint64_t j = j0; j <= j1; j++) L = max(L, common_level(keys[j], keys[j + m], dim, depth));
+  }
+  else if (n > m)
+  {
+    // large maxPts: count the points under the level-l ancestor by two binary searches; the count falls with l
+    int lo = 0, hi = depth - 1;  // the root holds all n > m points
+    while (lo < hi)
+    {
+      const int l = (lo + hi + 1) >> 1, sh = dim * (depth - l);
+      const uint64_t first = (keys[i] >> sh) << sh, last = first + ((1ull << sh) - 1);
+      uint64_t a = 0, b = n;  // lower bound of first
+      while (a < b) { const uint64_t mid = (a + b) >> 1; if (keys[mid] < first) a = mid + 1; else b = mid; }
+      uint64_t c = a, d = n;  // upper bound of last
+      while (c < d) { const uint64_t mid = (c + d) >> 1; if (keys[mid] <= last) c = mid + 1; else d = mid; }
+      if (c - a > m) lo = l;
+      else hi = l - 1;
+    }
+    L = lo;
   }
   L = min(L, depth - 1);
   const int l0 = i > 0 ? min(common_level(keys[i - 1], keys[i], dim, depth), L) : 0;
