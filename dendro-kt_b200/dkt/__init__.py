@@ -277,9 +277,10 @@ class DA:
         return xyz, lev
 
     def nodes(self):
-        """getTNCoords(): (xyz, level) of every CG node in DA order."""
-        xyz = np.zeros((self.n_nodes, self.dim), dtype=np.uint32)
-        lev = np.zeros(self.n_nodes, dtype=np.uint8)
+        """getTNCoords(): (xyz, level) of every CG node in DA order; partitioned DA: of the local vector [owned | ghosts]."""
+        n = self.n_nodes + self.n_ghost_nodes
+        xyz = np.zeros((n, self.dim), dtype=np.uint32)
+        lev = np.zeros(n, dtype=np.uint8)
         _check(lib().dkt_da_export_nodes(self._h, _ptr(xyz), _ptr(lev)))
         return xyz, lev
 

@@ -90,6 +90,8 @@ def main():
     n = da1.n_nodes
     u = cases.input_vector(n)
     v1 = da1.matvec(op, u)
+    nx1, nl1 = da1.nodes()
+    b1 = da1.boundary_ids()
     da1.close()
     daN = dkt.DA(xyz, lev, dim, 1, md, rank=rank, nranks=world, nccl_id=bcast_id(rank))
     vN = gathered_matvec(daN, op, u, n, rank, world)
@@ -97,6 +99,14 @@ def main():
     if rank == 0:
         print("4-D ball level 6: %d elements, %d nodes, ranks=%d: rel diff vs single GPU %.2e" % (da1.n_elem, n, world, err))
     ok &= err < 1e-12
+    # DA getters of a partitioned DA: node coordinates of the owned segment and the owned boundary nodes are the single-rank ones
+    nxN, nlN = daN.nodes()
+    oid = daN.owned_ids().astype(np.int64)
+    okg = len(nlN) == daN.n_nodes + daN.n_ghost_nodes and np.array_equal(nxN[:daN.n_nodes], nx1[oid]) and np.array_equal(nlN[:daN.n_nodes], nl1[oid])
+    okg &= np.array_equal(np.sort(oid[daN.boundary_ids().astype(np.int64)]), np.sort(np.intersect1d(oid, b1.astype(np.int64))))
+    if rank == 0:
+        print("partitioned DA getters (nodes, boundary ids):", "ok" if okg else "MISMATCH")
+    ok &= bool(okg)
     # (c) the ghost exchanges on their own (dkt_ghost_read/write): ghost copies equal the owners' values; a write-back of ones
     # adds, to every owned node, the number of ranks that ghost it
     ids = torch.from_numpy(daN.owned_ids().astype(np.int64)).cuda()
