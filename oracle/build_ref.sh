@@ -38,9 +38,10 @@ insert_after FEM/examples/src/heatVec.cpp 103 "out[bdyIndex[i]]=0.0;" "    retur
 insert_after FEM/examples/src/heatVec.cpp 92 "out[bdyIndex[i]]=0.0;" "    return true;"
 
 CXX=${CXX:-g++}
-FLAGS="-std=c++11 -O3 -DNDEBUG -w -fpermissive -fPIC -DWITH_BLAS_LAPACK -DUSE_64BIT_INDICES \
+SHIM=$HERE/shim   # build_variant switches it to shim_mp for the multi-process oracle
+FLAGS_TAIL="-std=c++11 -O3 -DNDEBUG -w -fpermissive -fPIC -DWITH_BLAS_LAPACK -DUSE_64BIT_INDICES \
  -DSPLITTER_SELECTION_FIX -DNUM_NPES_THRESHOLD=2 -DDENDRO_VTU_ASCII \
- -I$HERE/shim -I$W/include -I$W/FEM/include -I$W/array/include -I$W/FEM/examples/include -I$W/test"
+ -I$W/include -I$W/FEM/include -I$W/array/include -I$W/FEM/examples/include -I$W/test"
 SRCS="src/binUtils.cpp src/parUtils.cpp src/point.cpp src/profiler.cpp src/KDhcurvedata.cpp src/KDhcurvedata_DATA.cpp \
  src/tsort.cpp src/nsort.cpp src/treeNode.cpp src/oda.cpp FEM/src/tensor.cpp FEM/src/refel.cpp FEM/src/basis.cpp \
  FEM/examples/src/heatMat.cpp FEM/examples/src/heatVec.cpp"
@@ -48,8 +49,13 @@ SRCS="src/binUtils.cpp src/parUtils.cpp src/point.cpp src/profiler.cpp src/KDhcu
 build_variant() {
   local name=$1; shift
   local extra="$*"
+  local FLAGS="-I$SHIM $FLAGS_TAIL"
   mkdir -p "$W/obj_$name"
   local objs=""
+  if [ "$SHIM" = "$HERE/shim_mp" ]; then
+    $CXX -std=c++11 -O2 -fPIC -I$SHIM -c "$HERE/shim_mp/mpi_mp.cpp" -o "$W/obj_$name/mpi_mp.o" &
+    objs="$W/obj_$name/mpi_mp.o"
+  fi
   for s in $SRCS; do
     o=$W/obj_$name/$(echo "$s" | tr '/' '_').o
     $CXX $FLAGS $extra -c "$W/$s" -o "$o" &
@@ -63,3 +69,6 @@ build_variant() {
 }
 build_variant morton
 build_variant hilbert -DHILBERT_ORDERING
+# the same library over the multi-process MPI stand-in (oracle/shim_mp): the reference on several ranks, SURVEY 8f N3
+SHIM=$HERE/shim_mp
+build_variant mp_morton

@@ -318,6 +318,19 @@ extern "C"
     DABase *b = (DABase *)d;
     return DISPATCH(b->m_dim, da_boundary<2>(b, ids), da_boundary<3>(b, ids), da_boundary<4>(b, ids));
   }
+  /* out[0..5] = getLocalNodalSz, getLocalNodeBegin, getTotalNodalSz, getNpesAll, getRankAll, getGlobalNodeSz (several ranks) */
+  void dktref_da_local_info(void *d, long *out)
+  {
+    DABase *b = (DABase *)d;
+#define DKT_INFO(D)                                                                                                    \
+  {                                                                                                                    \
+    ot::DA<D> *da = static_cast<DAH<D> *>(b)->da;                                                                      \
+    out[0] = da->getLocalNodalSz(); out[1] = da->getLocalNodeBegin(); out[2] = da->getTotalNodalSz();                  \
+    out[3] = da->getNpesAll(); out[4] = da->getRankAll(); out[5] = (long)da->getGlobalNodeSz();                       \
+  }
+    if (b->m_dim == 2) DKT_INFO(2) else if (b->m_dim == 3) DKT_INFO(3) else DKT_INFO(4)
+#undef DKT_INFO
+  }
   void dktref_da_destroy(void *d) { delete (DABase *)d; }
 
   /* 1-D operators of the reference's RefElement(dim, order), row-major M x M, M = order+1. */
