@@ -204,6 +204,51 @@ def _reference_worker(idx, steps, warmup, level, barrier, out):
     out.put((idx, t0, t1, da.num_nodes, len(lev)))
 
 
+def _reference_mpi_job(rank, nranks, steps, warmup, level):
+    """One rank of ONE distributed reference job (oracle/shim_mp): a contiguous piece of the sorted sample tree, the reference's
+    distributed ot::DA, feMatrix::matVec with its ghost exchanges."""
+    import numpy as np
+    import dkt
+    import dktref
+    import dktref_mp
+    from dkt import operators
+    xyz, lev = dkt.trees.moving_ball_tree(DIM, level, MAX_DEPTH)
+    R = dktref_mp.session(DIM, MAX_DEPTH)
+    sx, sl = R.tree_from_elements(xyz, lev, sort=True).export()
+    n = len(sl)
+    lo, hi = rank * n // nranks, (rank + 1) * n // nranks
+    da = R.da(R.tree_from_elements(sx[lo:hi], sl[lo:hi], sort=False), ORDER)
+    info = dktref_mp.local_info(da)
+    K = operators.laplace_kref(DIM, ORDER)
+    u = np.random.default_rng(99 + rank).uniform(-1, 1, info[0])
+    da.matvec(u, dktref.OP_DENSE, K, alpha=DIM - 2.0, nwarm=warmup, niter=0)
+    t0 = time.perf_counter()
+    da.matvec(u, dktref.OP_DENSE, K, alpha=DIM - 2.0, nwarm=0, niter=steps)  # every matVec synchronises the ranks (ghost exchange)
+    return (time.perf_counter() - t0) / steps, info[0], info[2], info[5]
+
+
+def reference_mpi_mode(args, procs, level):
+    """The reference in its own parallel mode - ONE job, one rank per core, real ghost exchanges - over the multi-process MPI stand-in
+    of oracle/shim_mp.  Reported beside the replica number (which stays the line's value: it is the upper bound)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import dktref_mp
+        if not dktref_mp.available():
+            return {"unavailable": "oracle/_ref/libdktref_mp_morton.so is not built"}
+        ranks = max(1, min(procs, 16))
+        res = dktref_mp.run(ranks, _reference_mpi_job, args.steps, args.warmup, level, arena_bytes=1 << 33, timeout=900)
+        secs = max(r[0] for r in res)
+        n_global = res[0][3]
+        return {"ranks": ranks, "value": n_global / secs, "unit": UNIT, "ms_per_step": secs * 1e3, "n_nodes": n_global,
+                "owned_nodes_min_max": [min(r[1] for r in res), max(r[1] for r in res)],
+                "ghosted_nodes_min_max": [min(r[2] for r in res), max(r[2] for r in res)],
+                "how": "one distributed job of the reference (its own partitioned ot::DA and ghost exchange) on the same sample tree, "
+                       "ranks = processes over a shared-memory MPI stand-in (oracle/shim_mp); ONE tree shared by all cores, directly comparable with "
+                       "`value` (the replicas' aggregate)"}
+    except Exception as e:  # noqa: BLE001 - informational leg: never fails the arm
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path on the host cores.  The reference parallelises by
     MPI rank per core and has no threading in this path; the image has no MPI, so every core runs an
@@ -253,6 +298,7 @@ def run_reference(args):
                    "replicas": procs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_mpi": reference_mpi_mode(args, procs, level),
     }
     print(json.dumps(line))
 
