@@ -287,6 +287,17 @@ def run_reference(args):
     value = procs * n_nodes / secs
     sample = ("%d independent single-rank replicas (one per core; no MPI in the image) of the 4-D p=1 moving-ball tree at max_level %d "
               "(%d elements, %d nodes each), %d matvecs after %d warm-up" % (procs, level, n_elem, n_nodes, args.steps, args.warmup))
+    # The reference's real parallel mode is ONE job with a rank per core.  If that leg ran and is the faster of the two, it is the
+    # arm's number (the reference at its best on this box); the replicas' aggregate stays in the line for comparison.
+    replicas = {"value": value, "ms_per_step": secs * 1e3, "replicas": procs, "sample": sample}
+    mpi = reference_mpi_mode(args, procs, level)
+    mode = "replicas"
+    if "value" in mpi and mpi["value"] > value:
+        mode = "distributed"
+        value, secs, procs = mpi["value"], mpi["ms_per_step"] * 1e-3, mpi["ranks"]
+        sample = ("ONE distributed reference job, %d ranks (one per core) over the multi-process MPI stand-in oracle/shim_mp: the reference's own "
+                  "partitioned ot::DA and ghost exchanges on the 4-D p=1 moving-ball tree at max_level %d (%d elements, %d nodes), %d matvecs "
+                  "after %d warm-up" % (procs, level, n_elem, n_nodes, args.steps, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -295,10 +306,11 @@ def run_reference(args):
                                "max_depth %d: the bench tree's generator at the largest level the reference builds and runs within about "
                                "a minute per core" % (level, MAX_DEPTH),
                    "dim": DIM, "order": ORDER, "n_elem": n_elem, "n_nodes": n_nodes, "n_hanging_elem": n_hang, "tree_class": tree_class,
-                   "replicas": procs},
+                   "mode": mode, "cores": procs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "reference_mpi": reference_mpi_mode(args, procs, level),
+        "reference_replicas": replicas,
+        "reference_mpi": mpi,
     }
     print(json.dumps(line))
 
