@@ -126,11 +126,15 @@ def test_reference_arm_json_contract():
     import dktref
     if not dktref.available("morton"):
         pytest.skip("oracle/_ref not built")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-procs", "2"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-procs", "2",
+                          "--ref-level", "4"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "DOF/s" and line["value"] > 0 and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in line["config"]
+    assert "workload" in line["config"] and line["config"]["mode"] in ("replicas", "distributed")
+    assert line["reference_replicas"]["replicas"] == 2 and line["reference_replicas"]["value"] > 0
+    mpi = line["reference_mpi"]  # ONE distributed job over oracle/shim_mp (or the reason it could not run)
+    assert ("value" in mpi and mpi["ranks"] == 2 and mpi["n_nodes"] == line["config"]["n_nodes"]) or "unavailable" in mpi
