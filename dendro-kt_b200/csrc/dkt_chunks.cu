@@ -1311,9 +1311,13 @@ __device__ __forceinline__ void xor_unpermute(T *v, int c)
 // the interpolation becomes child-independent up to the J-conjugated matrix ipx, so those paths
 // work in permuted coordinates throughout; the dense path un-permutes the slot words first.
 template <int DIM, int ORDER, int OPKIND, bool DIRI, bool HANG, int TPB, int NPT, bool EXIP>
-__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE && OPKIND != DKT_OP_KRON) ? (HANG ? DKT_HANG_MINB : DKT_REG_MINB) * (256 / DKT_ROWS) : 2)) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
+__global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIND != DKT_OP_DENSE && OPKIND != DKT_OP_KRON) ? (HANG ? DKT_HANG_MINB : DKT_REG_MINB) * (256 / DKT_ROWS) : ((DKT_MV3_LEAN && Mv3Params<DIM, ORDER>::N > 16) ? 3 : 2))) k_mv3(const __grid_constant__ Mv3Params<DIM, ORDER> p)
 {
   constexpr int N = Mv3Params<DIM, ORDER>::N;
+  // Order 2 (27 nodes per element): the element phase alone needs ~110 registers, so the node records of the current and the
+  // next chunk (2 x NPT ids + flags per thread) are NOT kept in registers: the gather and the node phase read them from
+  // global memory where they are needed (the second read hits L2).  3 CTAs per SM instead of 2.
+  constexpr bool LEAN = DKT_MV3_LEAN && N > 16;
   constexpr int M = ORDER + 1;
   constexpr int ROWS = HANG ? 2 : 1;
   DKT_DYN_SMEM(double, sm);
@@ -1326,9 +1330,10 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
   if (c >= p.nChunks) return;
   const uint32_t E = p.elemsPerChunk;
 
-  uint32_t gidC[NPT], gidN[NPT];
-  uint16_t metaC[NPT], metaN[NPT];
+  uint32_t gidC[LEAN ? 1 : NPT], gidN[LEAN ? 1 : NPT];
+  uint16_t metaC[LEAN ? 1 : NPT], metaN[LEAN ? 1 : NPT];
   auto load_nodes = [&](uint64_t oa, uint64_t ob, uint32_t *g, uint16_t *m) {
+    if (LEAN) return;
     const int nloc = (int)(ob - oa);
 #pragma unroll
     for (int k = 0; k < NPT; k++)
@@ -1341,6 +1346,17 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
         g[k] = p.gid[oa + n];
         m[k] = p.meta[oa + n];
       }
+    }
+  };
+  auto issue_gather_lean = [&](double *un, uint64_t oa, int nloc) {
+    if (tid == 0) un[nloc] = 0.0;
+#pragma unroll 4
+    for (int n = tid; n < nloc; n += TPB)
+    {
+      const uint16_t m = p.meta[oa + n];
+      if (!(m & META_PRESENT)) continue;
+      if (DIRI && (m & META_BDY)) un[n] = 0.0;
+      else cp_async8(un + n, p.in + p.gid[oa + n]);
     }
   };
   auto issue_gather = [&](double *un, const uint32_t *g, const uint16_t *m, int nloc) {
@@ -1387,7 +1403,8 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
   // ---- prologue: everything for the first chunk ------------------------------------------------
   uint64_t offA = p.node_off[c], offB = p.node_off[c + 1];
   load_nodes(offA, offB, gidC, metaC);
-  issue_gather(unb, gidC, metaC, (int)(offB - offA));
+  if (LEAN) issue_gather_lean(unb, offA, (int)(offB - offA));
+  else issue_gather(unb, gidC, metaC, (int)(offB - offA));
   cp_async_commit();
   for (int k = tid; k < (int)p.jdStride; k += TPB) jdb[k] = p.jd[c * (uint64_t)p.jdStride + k];
   load_slots(c);
@@ -1490,13 +1507,32 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
     // T3: start the next chunk's gather and index loads; they land during T4
     if (hasN)
     {
-      issue_gather(unb + (buf ^ 1) * p.ncap, gidN, metaN, (int)(offNB - offNA));
+      if (LEAN) issue_gather_lean(unb + (buf ^ 1) * p.ncap, offNA, (int)(offNB - offNA));
+      else issue_gather(unb + (buf ^ 1) * p.ncap, gidN, metaN, (int)(offNB - offNA));
       int *jdn = jdb + (buf ^ 1) * p.jdStride;
       for (int k = tid; k < (int)p.jdStride; k += TPB) jdn[k] = p.jd[cn * (uint64_t)p.jdStride + k];
       load_slots(cn);
     }
     cp_async_commit();
     __syncthreads();  // T4: X complete
+    if (LEAN)
+    {
+      const int nlocC = (int)(offB - offA);
+#pragma unroll 2
+      for (int n = tid; n < nlocC; n += TPB)
+      {
+        const uint32_t m = p.meta[offA + n];
+        const int len = m & META_LEN;
+        if (len == 0) continue;  // absent, or only read by this chunk
+        double acc = X[n];  // jd[0] == 0
+        for (int j = 1; j < len; j++) acc += X[jd[j] + n];
+        if (DIRI && (m & META_BDY)) continue;
+        const uint32_t g = p.gid[offA + n];
+        if (m & META_SHARED) atomicAdd(p.out + g, acc);
+        else p.out[g] = acc;
+      }
+    }
+    else
 #pragma unroll
     for (int k = 0; k < NPT; k++)
     {
@@ -1522,8 +1558,13 @@ __global__ void __launch_bounds__(TPB, ((Mv3Params<DIM, ORDER>::N <= 16 && OPKIN
     c = cn;
     cn = cnn;
     hasN = cn < p.nChunks;
+    if (!LEAN)
+    {
 #pragma unroll
-    for (int k = 0; k < NPT; k++) { gidC[k] = gidN[k]; metaC[k] = metaN[k]; }
+      for (int k = 0; k < NPT; k++) { gidC[k] = gidN[k]; metaC[k] = metaN[k]; }
+    }
+    offA = offNA;
+    offB = offNB;
     offNA = offNNA;
     offNB = offNNB;
     buf ^= 1;

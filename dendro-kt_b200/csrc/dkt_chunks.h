@@ -30,6 +30,9 @@ namespace dkt
     }                                                                                                \
   } while (0)
 
+#ifndef DKT_MV3_LEAN
+#define DKT_MV3_LEAN 1  // order-2 per-element kernels: node records read where needed instead of kept in registers (3 CTAs/SM)
+#endif
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;                       // 4096 slots per chunk
 constexpr int SLOT_CAP = SORT_THREADS * SORT_ITEMS;
