@@ -42,6 +42,17 @@ def test_dist_api_program_compiles(dkt, tmp_path):
                            "-L", LIBDIR, "-ldkt", "-Wl,-rpath," + LIBDIR])
 
 
+def test_mpi_branch_of_the_headers_compiles(dkt, tmp_path):
+    """CPU: the image has no MPI, but oracle/shim_mp declares the MPI subset the reference uses.  Compiling the multi-rank test
+    program with -DDKT_HAVE_MPI against it type-checks the MPI branch of ot::DA / dkt_host (MPI_Comm_rank/size, MPI_Allgatherv of
+    the tree pieces, MPI_Bcast of the NCCL id), warning-free."""
+    shim = os.path.join(ROOT, "oracle", "shim_mp")
+    out = str(tmp_path / "test_dist_api_mpi")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-DDKT_HAVE_MPI", "-include", os.path.join(shim, "mpi.h"), "-I", shim, "-I", INC,
+                           os.path.join(ROOT, "tests", "cpp", "test_dist_api.cpp"), os.path.join(shim, "mpi_mp.cpp"), "-o", out,
+                           "-L", LIBDIR, "-ldkt", "-Wl,-rpath," + LIBDIR])
+
+
 def test_host_api_compiles(host_api_binary):
     """CPU: the header-only host layer compiles warning-free against the C ABI and links to libdkt.so."""
     assert os.path.exists(host_api_binary)
