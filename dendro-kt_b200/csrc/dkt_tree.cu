@@ -131,10 +131,12 @@ __device__ inline int common_level(uint64_t a, uint64_t b, int dim, int depth)
   return depth - 1 - h / dim;
 }
 
-__global__ void k_point_keys(const uint32_t *pts, uint64_t n, int dim, int depth, uint64_t *keys)
+__global__ void k_point_keys(const uint32_t *pts, uint64_t n, int dim, int depth, uint64_t *keys, int *outside)
 {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  for (int d = 0; d < dim; d++)
+    if ((uint64_t)pts[i * dim + d] >> depth) *outside = 1;  // benign race: every writer stores 1
   keys[i] = node_key(pts + i * dim, dim, depth, depth);
 }
 
@@ -399,7 +401,14 @@ int build_tree(Tree &tr, const uint32_t *pts, uint64_t n, uint64_t maxPts, bool 
   {
     TBuf<uint64_t> k0;
     CK(k0.alloc(n)); CK(keys.alloc(n));
-    TLAUNCH(k_point_keys, n, src, n, dim, depth, k0.p);
+    TBuf<int> outside;
+    CK(outside.alloc(1));
+    CK(cudaMemsetAsync(outside.p, 0, sizeof(int), stream));
+    TLAUNCH(k_point_keys, n, src, n, dim, depth, k0.p, outside.p);
+    int h_out = 0;
+    CK(cudaMemcpyAsync(&h_out, outside.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (h_out) { set_error("dkt_tree_from_points: a point coordinate is outside [0, 2^max_depth)"); return DKT_ERR_INVALID; }
     int rc = sort_keys(stream, k0.p, keys.p, n, dim * depth);
     if (rc) return rc;
   }
